@@ -1,0 +1,303 @@
+// C-ABI entry points of libf3dgs_b200.so and the host-side orchestration of one view.
+// Mirrors CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (reference rasterizer_impl.cu:198-342, :347-461, :141-153); see include/f3dgs_b200.h.
+//
+// Per forward call: 1 preprocess kernel, cub::DeviceScan::InclusiveSum, ONE 4-byte D2H copy +
+// stream sync (num_rendered sizes the binning buffer and is returned to the caller, as in the
+// reference rasterizer_impl.cu:283), key emission, cub::DeviceRadixSort::SortPairs on the
+// minimal key width, range detection, composite.  Everything is enqueued on the caller's stream.
+#include <cub/cub.cuh>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/f3dgs_b200.h"
+#include "kernels.h"
+
+namespace f3dgs {
+unsigned long long g_launches = 0;
+}
+using namespace f3dgs;
+
+namespace {
+
+thread_local std::string t_error;
+
+int fail(int code, const std::string& msg) {
+    t_error = msg;
+    return -code;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct GeomLayout {
+    size_t rec, cov3d, clamped, tiles, offsets, radii, fixed_bytes;
+    explicit GeomLayout(size_t P) {
+        size_t o = 0;
+        rec = o;      o = align_up(o + P * sizeof(SplatRec));
+        cov3d = o;    o = align_up(o + P * 6 * sizeof(float));
+        clamped = o;  o = align_up(o + P);
+        tiles = o;    o = align_up(o + P * 4);
+        offsets = o;  o = align_up(o + P * 4);
+        radii = o;    o = align_up(o + P * 4);
+        fixed_bytes = o;
+    }
+};
+struct ImgLayout {
+    size_t final_T, n_contrib, ranges, bytes;
+    ImgLayout(size_t HW, size_t tiles) {
+        size_t o = 0;
+        final_T = o;    o = align_up(o + HW * 4);
+        n_contrib = o;  o = align_up(o + HW * 4);
+        ranges = o;     o = align_up(o + tiles * 8);
+        bytes = o;
+    }
+};
+struct BinLayout {
+    size_t point_list, keys, point_list_unsorted, keys_unsorted, fixed_bytes;
+    explicit BinLayout(size_t R) {
+        size_t o = 0;
+        point_list = o;           o = align_up(o + R * 4);
+        keys = o;                 o = align_up(o + R * 8);
+        point_list_unsorted = o;  o = align_up(o + R * 4);
+        keys_unsorted = o;        o = align_up(o + R * 8);
+        fixed_bytes = o;
+    }
+};
+
+inline int bit_length(uint32_t n) {
+    int b = 0;
+    while (n) {
+        b++;
+        n >>= 1;
+    }
+    return b;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(F3DGS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+// reference CHECK_CUDA (auxiliary.h:172-179): in debug mode synchronise and surface errors per stage
+#define STAGE_CHECK(name)                                                                           \
+    do {                                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                        \
+        if (e_ == cudaSuccess && debug) e_ = cudaStreamSynchronize(stream);                         \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(F3DGS_ERR_CUDA, std::string("stage ") + name + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+ViewParams make_view(int P, int D, int M, int C, int width, int height, float tan_fovx, float tan_fovy,
+                     float scale_modifier, const float* viewmatrix, const float* projmatrix,
+                     const float* cam_pos) {
+    ViewParams vp;
+    vp.P = P; vp.D = D; vp.M = M; vp.C = C; vp.W = width; vp.H = height;
+    vp.grid_x = (uint32_t)((width + F3DGS_TILE - 1) / F3DGS_TILE);
+    vp.grid_y = (uint32_t)((height + F3DGS_TILE - 1) / F3DGS_TILE);
+    vp.tan_fovx = tan_fovx; vp.tan_fovy = tan_fovy;
+    vp.focal_y = height / (2.0f * tan_fovy);  // reference rasterizer_impl.cu:225-226
+    vp.focal_x = width / (2.0f * tan_fovx);
+    vp.scale_modifier = scale_modifier;
+    vp.viewmatrix = viewmatrix; vp.projmatrix = projmatrix; vp.cam_pos = cam_pos;
+    return vp;
+}
+
+}  // namespace
+
+extern "C" {
+
+int f3dgs_abi_version(void) { return F3DGS_ABI_VERSION; }
+const char* f3dgs_last_error(void) { return t_error.c_str(); }
+unsigned long long f3dgs_launch_count(void) { return g_launches; }
+
+int f3dgs_get_layout(int P, int width, int height, int R, f3dgs_layout* out) {
+    if (!out || P < 0 || width <= 0 || height <= 0 || R < 0)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_get_layout: bad argument");
+    const GeomLayout g((size_t)P);
+    const size_t tiles = (size_t)((width + 15) / 16) * ((height + 15) / 16);
+    const ImgLayout im((size_t)width * height, tiles);
+    const BinLayout b((size_t)R);
+    out->geom_bytes = g.fixed_bytes; out->geom_rec = g.rec; out->geom_cov3d = g.cov3d;
+    out->geom_clamped = g.clamped; out->geom_tiles = g.tiles; out->geom_offsets = g.offsets;
+    out->geom_radii = g.radii;
+    out->img_bytes = im.bytes; out->img_final_T = im.final_T; out->img_n_contrib = im.n_contrib;
+    out->img_ranges = im.ranges;
+    out->bin_bytes = b.fixed_bytes; out->bin_point_list = b.point_list; out->bin_keys = b.keys;
+    return 0;
+}
+
+int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc_fn binning_alloc,
+                  void* binning_ctx, f3dgs_alloc_fn image_alloc, void* image_ctx, int P, int D, int M, int C,
+                  const float* background, int width, int height, const float* means3D, const float* shs,
+                  const float* colors_precomp, const float* semantic_feature, const float* opacities,
+                  const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                  const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                  float tan_fovy, int prefiltered, float* out_color, float* out_feature_map, float* out_depth,
+                  int* radii, int debug, void* cuda_stream) {
+    t_error.clear();
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (P < 0 || width <= 0 || height <= 0 || C < 0 || C > F3DGS_MAX_FEATURE_DIM || D < 0 || D > 3)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_forward: bad sizes (P, width, height, C or D)");
+    if (!geometry_alloc || !binning_alloc || !image_alloc)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_forward: missing allocator");
+    if (P == 0) return 0;
+    if (!means3D || !opacities || !background || !viewmatrix || !projmatrix || !cam_pos || !out_color ||
+        !out_depth)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_forward: NULL required pointer");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_forward: provide exactly one of shs / colors_precomp");
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT,
+                    "f3dgs_forward: provide exactly one of (scales, rotations) / cov3D_precomp");
+    if (C > 0 && (!semantic_feature || !out_feature_map))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_forward: C > 0 needs semantic_feature and out_feature_map");
+    if (shs && M < (D + 1) * (D + 1))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_forward: M < (D+1)^2 SH coefficients");
+
+    const ViewParams vp = make_view(P, D, M, C, width, height, tan_fovx, tan_fovy, scale_modifier, viewmatrix,
+                                    projmatrix, cam_pos);
+    const size_t tiles = (size_t)vp.grid_x * vp.grid_y;
+
+    // ---- geometry buffer
+    const GeomLayout gl((size_t)P);
+    size_t scan_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, P, stream));
+    char* geom = geometry_alloc(geometry_ctx, gl.fixed_bytes + align_up(scan_bytes));
+    if (!geom) return fail(F3DGS_ERR_ALLOC, "geometry allocator returned NULL");
+    SplatRec* rec = reinterpret_cast<SplatRec*>(geom + gl.rec);
+    float* cov3d = reinterpret_cast<float*>(geom + gl.cov3d);
+    uint8_t* clamped = reinterpret_cast<uint8_t*>(geom + gl.clamped);
+    uint32_t* tiles_touched = reinterpret_cast<uint32_t*>(geom + gl.tiles);
+    uint32_t* offsets = reinterpret_cast<uint32_t*>(geom + gl.offsets);
+    int* radii_int = reinterpret_cast<int*>(geom + gl.radii);
+    if (radii == nullptr) radii = radii_int;  // reference rasterizer_impl.cu:232-235
+
+    // ---- image buffer
+    const ImgLayout il((size_t)width * height, tiles);
+    char* img = image_alloc(image_ctx, il.bytes);
+    if (!img) return fail(F3DGS_ERR_ALLOC, "image allocator returned NULL");
+    float* final_T = reinterpret_cast<float*>(img + il.final_T);
+    uint32_t* n_contrib = reinterpret_cast<uint32_t*>(img + il.n_contrib);
+    uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
+
+    launch_preprocess_fwd(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                          prefiltered != 0, radii, rec, cov3d, clamped, tiles_touched, stream);
+    STAGE_CHECK("preprocess");
+
+    CUDA_TRY(cub::DeviceScan::InclusiveSum(geom + gl.fixed_bytes, scan_bytes, tiles_touched, offsets, P, stream));
+    g_launches += 2;
+    STAGE_CHECK("scan");
+
+    static thread_local int* h_count = nullptr;
+    if (!h_count) CUDA_TRY(cudaHostAlloc((void**)&h_count, sizeof(int), cudaHostAllocDefault));
+    CUDA_TRY(cudaMemcpyAsync(h_count, offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const int R = *h_count;
+    if (R < 0) return fail(F3DGS_ERR_CUDA, "num_rendered overflowed int32");
+
+    // ---- binning buffer
+    const BinLayout bl((size_t)R);
+    const int end_bit = 32 + bit_length((uint32_t)(tiles > 0 ? tiles - 1 : 0));
+    size_t sort_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr,
+                                             (uint32_t*)nullptr, (uint32_t*)nullptr, R, 0, end_bit, stream));
+    char* bin = binning_alloc(binning_ctx, bl.fixed_bytes + align_up(sort_bytes));
+    if (!bin) return fail(F3DGS_ERR_ALLOC, "binning allocator returned NULL");
+    uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(bin + bl.keys);
+    uint32_t* point_list_unsorted = reinterpret_cast<uint32_t*>(bin + bl.point_list_unsorted);
+    uint64_t* keys_unsorted = reinterpret_cast<uint64_t*>(bin + bl.keys_unsorted);
+
+    CUDA_TRY(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), stream));
+    if (R > 0) {
+        launch_duplicate_keys(P, rec, offsets, radii, vp.grid_x, vp.grid_y, keys_unsorted, point_list_unsorted,
+                              stream);
+        STAGE_CHECK("duplicate_keys");
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin + bl.fixed_bytes, sort_bytes, keys_unsorted, keys,
+                                                 point_list_unsorted, point_list, R, 0, end_bit, stream));
+        g_launches += (unsigned long long)((end_bit + 7) / 8 + 2);
+        STAGE_CHECK("sort");
+        launch_tile_ranges(R, keys, ranges, stream);
+        STAGE_CHECK("tile_ranges");
+    }
+
+    cudaError_t e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T,
+                                         n_contrib, out_color, out_feature_map, out_depth, stream);
+    if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_fwd launch: ") + cudaGetErrorString(e));
+    STAGE_CHECK("composite_fwd");
+    return R;
+}
+
+int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, int width, int height,
+                   const float* means3D, const float* shs, const float* colors_precomp,
+                   const float* semantic_feature, const float* scales, float scale_modifier,
+                   const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                   const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                   const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                   const float* dL_dpix, const float* dL_dfeaturepix, const float* dL_depths, float* dL_dmean2D,
+                   float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dsemantic_feature,
+                   float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                   float* dL_dz, int debug, void* cuda_stream) {
+    (void)semantic_feature;  // not needed: dL/dfeature depends only on the blend weights
+    (void)colors_precomp;    // colours were copied into the per-Gaussian records by the forward
+    t_error.clear();
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (P < 0 || width <= 0 || height <= 0 || C < 0 || C > F3DGS_MAX_FEATURE_DIM || R < 0)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: bad sizes");
+    if (P == 0) return 0;
+    if (!geom_buffer || !binning_buffer || !image_buffer)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: missing forward buffers");
+    if (!dL_dpix || !dL_depths || (C > 0 && (!dL_dfeaturepix || !dL_dsemantic_feature)) || !dL_dmean2D ||
+        !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dz)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: NULL gradient pointer");
+    if (shs && !dL_dsh) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: shs given but dL_dsh NULL");
+    if (scales && (!rotations || !dL_dscale || !dL_drot))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: scales given but rotations/dL_dscale/dL_drot NULL");
+
+    const ViewParams vp = make_view(P, D, M, C, width, height, tan_fovx, tan_fovy, scale_modifier, viewmatrix,
+                                    projmatrix, cam_pos);
+    const size_t tiles = (size_t)vp.grid_x * vp.grid_y;
+    const GeomLayout gl((size_t)P);
+    const ImgLayout il((size_t)width * height, tiles);
+    const BinLayout bl((size_t)R);
+    const SplatRec* rec = reinterpret_cast<const SplatRec*>(geom_buffer + gl.rec);
+    const float* cov3d = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom_buffer + gl.cov3d);
+    const uint8_t* clamped = reinterpret_cast<const uint8_t*>(geom_buffer + gl.clamped);
+    if (radii == nullptr) radii = reinterpret_cast<const int*>(geom_buffer + gl.radii);
+    const float* final_T = reinterpret_cast<const float*>(image_buffer + il.final_T);
+    const uint32_t* n_contrib = reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib);
+    const uint2* ranges = reinterpret_cast<const uint2*>(image_buffer + il.ranges);
+    const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list);
+
+    cudaError_t e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,
+                                         dL_dfeaturepix, dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                         dL_dsemantic_feature, dL_dz, stream);
+    if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_bwd launch: ") + cudaGetErrorString(e));
+    STAGE_CHECK("composite_bwd");
+
+    launch_preprocess_bwd(vp, means3D, radii, shs, clamped, scales, rotations, cov3d, dL_dmean2D, dL_dconic,
+                          dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, stream);
+    STAGE_CHECK("preprocess_bwd");
+    return 0;
+}
+
+int f3dgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                       uint8_t* present, void* cuda_stream) {
+    (void)projmatrix;  // the reference's frustum side test is commented out (auxiliary.h:160)
+    t_error.clear();
+    if (P < 0) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_mark_visible: P < 0");
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !present)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_mark_visible: NULL pointer");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    launch_mark_visible(P, means3D, viewmatrix, present, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("mark_visible: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

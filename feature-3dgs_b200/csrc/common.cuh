@@ -1,0 +1,132 @@
+// Shared device helpers for the f3dgs_b200 kernels (sm_100a).
+//
+// Numerics contract.  The tile/key indexing of this library must be bit-identical to the
+// reference extension built by nvcc with default flags (-fmad=true, IEEE div/sqrt).  nvcc
+// decides where a*b+c becomes an FMA; that placement was read off the PTX of the reference's
+// preprocess and render kernels and is reproduced here with explicit round-to-nearest
+// intrinsics (__fmaf_rn/__fmul_rn/__fadd_rn/...), which the compiler never re-associates or
+// contracts.  The CPU oracle (oracle/f3dgs_oracle.c) states the same operation sequence with
+// fmaf(), so all three agree bit for bit on everything that does not involve expf().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define F3DGS_TILE_X 16
+#define F3DGS_TILE_Y 16
+
+namespace f3dgs {
+
+// ---------------------------------------------------------------- exact fp32 building blocks
+__device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmar(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float divr(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float rcpr(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ float sqrtr(float a) { return __fsqrt_rn(a); }
+
+// a0*b0 + a1*b1 + a2*b2 as nvcc contracts it in the reference (GLM mat3 products, dot(),
+// transformPoint): the middle product is a plain multiply, the other two are fused.
+__device__ __forceinline__ float dot3r(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return fmar(a2, b2, fmar(a0, b0, mulr(a1, b1)));
+}
+
+// reference auxiliary.h:58-66 (transformPoint4x3), row `r` of the column-major 4x4
+__device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y, float z) {
+    return addr(m[12 + r], fmar(z, m[8 + r], fmar(x, m[r], mulr(y, m[4 + r]))));
+}
+
+// reference auxiliary.h:41-44 (ndc2Pix): evaluated in double because of the unsuffixed literals
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+    double t = __fma_rn(__dadd_rn((double)v, 1.0), (double)S, -1.0);
+    return (float)__dmul_rn(t, 0.5);
+}
+
+// reference auxiliary.h:46-56 (getRect)
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, uint32_t gx, uint32_t gy,
+                                          uint32_t& x0, uint32_t& y0, uint32_t& x1, uint32_t& y1) {
+    const float rf = (float)radius;
+    x0 = min(gx, (uint32_t)max(0, (int)mulr(subr(px, rf), 0.0625f)));
+    y0 = min(gy, (uint32_t)max(0, (int)mulr(subr(py, rf), 0.0625f)));
+    x1 = min(gx, (uint32_t)max(0, (int)mulr(addr(addr(addr(px, rf), 16.0f), -1.0f), 0.0625f)));
+    y1 = min(gy, (uint32_t)max(0, (int)mulr(addr(addr(addr(py, rf), 16.0f), -1.0f), 0.0625f)));
+}
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------- vector global access
+__device__ __forceinline__ void st_na_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f1(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Per-Gaussian record produced by the forward preprocess and consumed by both composites.
+// 48 bytes, three 16-byte words so it can be moved with 128-bit accesses.
+struct __align__(16) SplatRec {
+    float x, y;        // pixel-space mean (reference geom.means2D)
+    float ex, ey;      // conservative half extents of the region where alpha >= 1/255
+    float ca, cb, cc;  // conic (reference geom.conic_opacity.xyz)
+    float op;          // opacity (conic_opacity.w)
+    float r, g, b;     // colour after SH eval/clamp, or colors_precomp
+    float depth;       // view-space z (reference geom.depths)
+};
+
+}  // namespace f3dgs

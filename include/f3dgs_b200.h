@@ -1,0 +1,146 @@
+/*
+ * f3dgs_b200 -- C ABI of the B200-native feature-Gaussian rasterizer (libf3dgs_b200.so).
+ *
+ * This is the drop-in boundary below the Python/torch surface.  Every entry point takes plain
+ * device pointers and sizes -- no torch, no C++ types -- and replaces one member of the
+ * reference's inner C++ interface `CudaRasterizer::Rasterizer`
+ * (reference: submodules/diff-gaussian-rasterization-feature/cuda_rasterizer/rasterizer.h:18-94).
+ *
+ *   reference                                     this library
+ *   Rasterizer::forward      rasterizer.h:31-58   f3dgs_forward
+ *   Rasterizer::backward     rasterizer.h:60-93   f3dgs_backward
+ *   Rasterizer::markVisible  rasterizer.h:24-29   f3dgs_mark_visible
+ *
+ * Differences from the reference interface, all additive:
+ *   - the feature width C (reference: compile-time NUM_SEMANTIC_CHANNELS, config.h:16) is a
+ *     run-time argument, 0 <= C <= F3DGS_MAX_FEATURE_DIM;
+ *   - the three std::function<char*(size_t)> allocators become (function pointer, context) pairs;
+ *   - every call takes the CUDA stream to launch on (reference: legacy default stream);
+ *   - errors are returned as negative codes with a message in f3dgs_last_error() instead of C++
+ *     exceptions (reference: std::runtime_error from CHECK_CUDA, auxiliary.h:172-179).
+ *
+ * All float tensors are fp32, contiguous, device memory.  Matrices are the 16 floats of the
+ * reference's row-major [4,4] torch tensors, i.e. column-major for the kernels
+ * (auxiliary.h:58-77).  An absent optional input is a NULL pointer
+ * (rasterize_points.cu: empty tensor -> nullptr).
+ */
+#ifndef F3DGS_B200_H_INCLUDED
+#define F3DGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F3DGS_ABI_VERSION 1
+#define F3DGS_MAX_FEATURE_DIM 4096
+#define F3DGS_TILE 16 /* BLOCK_X == BLOCK_Y == 16, reference config.h:18-19 */
+
+/* error codes (returned negated) */
+#define F3DGS_OK 0
+#define F3DGS_ERR_INVALID_ARGUMENT 1
+#define F3DGS_ERR_CUDA 2
+#define F3DGS_ERR_ALLOC 3
+
+/* Allocator callback: must return device memory of at least `bytes` bytes, 256-byte aligned,
+ * valid until the matching backward call has finished (reference: the resize lambdas of
+ * rasterize_points.cu:27-33).  Called exactly once per buffer per forward: geometry first,
+ * image second, binning third (after the single host sync on num_rendered). */
+typedef char* (*f3dgs_alloc_fn)(void* ctx, size_t bytes);
+
+/* ---- forward: reference Rasterizer::forward, rasterizer_impl.cu:198-342 -------------------
+ * Returns num_rendered (>= 0; number of (Gaussian, tile) instances) or -(error code).
+ *   P            number of Gaussians           D  active SH degree (0..3)
+ *   M            SH coefficients per colour in `shs` (0 if shs == NULL)
+ *   C            feature width of semantic_feature / out_feature_map (run-time)
+ *   background   [3]            means3D [P,3]        shs [P,M,3] or NULL
+ *   colors_precomp [P,3] or NULL (exactly one of shs / colors_precomp)
+ *   semantic_feature [P,C] (NULL iff C == 0)         opacities [P]
+ *   scales [P,3] + rotations [P,4] (w,x,y,z), or cov3D_precomp [P,6]
+ *   viewmatrix, projmatrix [16]  cam_pos [3]
+ *   out_color [3,H,W]  out_feature_map [C,H,W]  out_depth [H,W]   (every element is written)
+ *   radii [P] int32 (may be NULL: kept internally)
+ *   debug != 0: synchronise and check after every stage (reference CHECK_CUDA semantics)
+ */
+int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx,
+                  f3dgs_alloc_fn binning_alloc, void* binning_ctx,
+                  f3dgs_alloc_fn image_alloc, void* image_ctx,
+                  int P, int D, int M, int C,
+                  const float* background, int width, int height,
+                  const float* means3D, const float* shs, const float* colors_precomp,
+                  const float* semantic_feature, const float* opacities,
+                  const float* scales, float scale_modifier, const float* rotations,
+                  const float* cov3D_precomp,
+                  const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                  float tan_fovx, float tan_fovy, int prefiltered,
+                  float* out_color, float* out_feature_map, float* out_depth, int* radii,
+                  int debug, void* cuda_stream);
+
+/* ---- backward: reference Rasterizer::backward, rasterizer_impl.cu:347-461 -----------------
+ * R is the num_rendered returned by the matching forward; the three buffers are the ones the
+ * allocators returned.  All dL_d* outputs must be ZERO-FILLED by the caller (the reference
+ * wrapper allocates them with torch::zeros, rasterize_points.cu:163-173); gradients are
+ * accumulated into them.  dL_dconic [P,4] and dL_dz [P] are scratch outputs like in the
+ * reference.  Returns 0 or -(error code).
+ */
+int f3dgs_backward(int P, int D, int M, int R, int C,
+                   const float* background, int width, int height,
+                   const float* means3D, const float* shs, const float* colors_precomp,
+                   const float* semantic_feature,
+                   const float* scales, float scale_modifier, const float* rotations,
+                   const float* cov3D_precomp,
+                   const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                   float tan_fovx, float tan_fovy, const int* radii,
+                   char* geom_buffer, char* binning_buffer, char* image_buffer,
+                   const float* dL_dpix, const float* dL_dfeaturepix, const float* dL_depths,
+                   float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                   float* dL_dsemantic_feature, float* dL_dmean3D, float* dL_dcov3D,
+                   float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_dz,
+                   int debug, void* cuda_stream);
+
+/* ---- markVisible: reference rasterizer_impl.cu:141-153 (checkFrustum :54-66) --------------
+ * present[i] = (view-space z of means3D[i] > 0.2).  `present` is P bytes (0/1). */
+int f3dgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                       const float* projmatrix, uint8_t* present, void* cuda_stream);
+
+/* ---- introspection for the parity harness --------------------------------------------------
+ * Byte offsets of the fields inside the three opaque buffers (the layout is private to this
+ * library; the reference's is rasterizer_impl.cu:154-194).  Offsets are relative to the
+ * 256-byte-aligned base pointer the allocator returned.
+ */
+typedef struct f3dgs_layout {
+    /* geometry buffer (P entries) */
+    size_t geom_bytes;
+    size_t geom_rec;        /* float4[3P]: {x,y,ext_x,ext_y} {conic a,b,c,opacity} {r,g,b,depth} */
+    size_t geom_cov3d;      /* float[6P] */
+    size_t geom_clamped;    /* uint8[P]  bit k set = colour channel k was clamped at 0 */
+    size_t geom_tiles;      /* uint32[P] tiles touched */
+    size_t geom_offsets;    /* uint32[P] inclusive scan of tiles touched */
+    size_t geom_radii;      /* int32[P]  internal radii */
+    /* image buffer */
+    size_t img_bytes;
+    size_t img_final_T;     /* float[H*W] */
+    size_t img_n_contrib;   /* uint32[H*W] */
+    size_t img_ranges;      /* uint2[tiles] */
+    /* binning buffer (R entries) */
+    size_t bin_bytes;
+    size_t bin_point_list;  /* uint32[R] sorted Gaussian ids */
+    size_t bin_keys;        /* uint64[R] sorted keys */
+} f3dgs_layout;
+
+int f3dgs_get_layout(int P, int width, int height, int R, f3dgs_layout* out);
+
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+unsigned long long f3dgs_launch_count(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char* f3dgs_last_error(void);
+
+int f3dgs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F3DGS_B200_H_INCLUDED */
