@@ -1,12 +1,15 @@
 // Shared device helpers for the f3dgs_b200 kernels (sm_100a).
 //
 // Numerics contract.  The tile/key indexing of this library must be bit-identical to the
-// reference extension built by nvcc with default flags (-fmad=true, IEEE div/sqrt).  nvcc
-// decides where a*b+c becomes an FMA; that placement was read off the PTX of the reference's
-// preprocess and render kernels and is reproduced here with explicit round-to-nearest
-// intrinsics (__fmaf_rn/__fmul_rn/__fadd_rn/...), which the compiler never re-associates or
-// contracts.  The CPU oracle (oracle/f3dgs_oracle.c) states the same operation sequence with
-// fmaf(), so all three agree bit for bit on everything that does not involve expf().
+// reference extension built by nvcc with default flags (-fmad=true, IEEE div/sqrt).  Where a*b+c
+// becomes an FMA is decided twice: by NVVM (visible in PTX as fma.rn) and again by ptxas, which
+// fuses un-suffixed mul.f32/add.f32 pairs it finds in the PTX.  Explicit _rn intrinsics would
+// block the second step, so the bit-exact stages (forward preprocess, the alpha/T recurrence of
+// the composite) are written as plain fp32 expressions with the same expression trees as the
+// reference's formulas and compiled by the same compiler with the same flags; bit-identity of
+// radii / keys / n_contrib / final_T / colour / depth against the reference build is then
+// checked on the GPU (tests/test_gpu_parity.py).  The CPU oracle (oracle/f3dgs_oracle.c)
+// restates the resulting operation sequence with fmaf().
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,19 +40,15 @@ __device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, f
 }
 
 // reference auxiliary.h:41-44 (ndc2Pix): evaluated in double because of the unsuffixed literals
-__device__ __forceinline__ float ndc2pix(float v, int S) {
-    double t = __fma_rn(__dadd_rn((double)v, 1.0), (double)S, -1.0);
-    return (float)__dmul_rn(t, 0.5);
-}
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
 
-// reference auxiliary.h:46-56 (getRect)
-__device__ __forceinline__ void tile_rect(float px, float py, int radius, uint32_t gx, uint32_t gy,
+// reference auxiliary.h:46-56 (getRect): float divide by the int tile size, truncation, clamp
+__device__ __forceinline__ void tile_rect(float px, float py, int max_radius, uint32_t gx, uint32_t gy,
                                           uint32_t& x0, uint32_t& y0, uint32_t& x1, uint32_t& y1) {
-    const float rf = (float)radius;
-    x0 = min(gx, (uint32_t)max(0, (int)mulr(subr(px, rf), 0.0625f)));
-    y0 = min(gy, (uint32_t)max(0, (int)mulr(subr(py, rf), 0.0625f)));
-    x1 = min(gx, (uint32_t)max(0, (int)mulr(addr(addr(addr(px, rf), 16.0f), -1.0f), 0.0625f)));
-    y1 = min(gy, (uint32_t)max(0, (int)mulr(addr(addr(addr(py, rf), 16.0f), -1.0f), 0.0625f)));
+    x0 = min(gx, (uint32_t)max((int)0, (int)((px - max_radius) / F3DGS_TILE_X)));
+    y0 = min(gy, (uint32_t)max((int)0, (int)((py - max_radius) / F3DGS_TILE_Y)));
+    x1 = min(gx, (uint32_t)max((int)0, (int)((px + max_radius + F3DGS_TILE_X - 1) / F3DGS_TILE_X)));
+    y1 = min(gy, (uint32_t)max((int)0, (int)((py + max_radius + F3DGS_TILE_Y - 1) / F3DGS_TILE_Y)));
 }
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX

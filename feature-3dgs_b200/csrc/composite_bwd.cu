@@ -225,12 +225,12 @@ composite_bwd_kernel(int W, int H, int C, const uint2* __restrict__ ranges,
                     if (kk[u] >= 0) {
                         const float4 r0 = st.rec0[kk[u]];
                         const float4 r1 = st.rec1[kk[u]];
-                        const float dx = subr(r0.x, pxf), dy = subr(r0.y, pyf);
-                        const float t4 = fmar(dx, mulr(dx, r1.x), mulr(dy, mulr(dy, r1.z)));
-                        const float power = subr(mulr(t4, -0.5f), mulr(dy, mulr(dx, r1.y)));
+                        // same expression trees as reference backward.cu:525-535
+                        const float dx = r0.x - pxf, dy = r0.y - pyf;
+                        const float power = -0.5f * (r1.x * dx * dx + r1.z * dy * dy) - r1.y * dx * dy;
                         if (!(power > 0.0f)) {
                             const float Gs = expf(power);
-                            const float a = fminf(mulr(r1.w, Gs), 0.99f);
+                            const float a = fminf(0.99f, r1.w * Gs);
                             if (!(a < 1.0f / 255.0f)) {
                                 al[u] = a; Gv[u] = Gs; dxv[u] = dx; dyv[u] = dy;
                             }
@@ -251,7 +251,7 @@ composite_bwd_kernel(int W, int H, int C, const uint2* __restrict__ ranges,
                         const float4 r1 = st.rec1[k];
                         const float4 r2 = st.rec2[k];
                         const float one_m_a = 1.f - alpha;
-                        T = divr(T, one_m_a);
+                        T = T / one_m_a;
                         wgt = alpha * T;
                         float dL_dalpha = 0.f;
                         const float col[3] = {r2.x, r2.y, r2.z};

@@ -123,11 +123,11 @@ composite_fwd_kernel(int W, int H, int C, const uint2* __restrict__ ranges,
                     if (kk[u] >= 0) {
                         const float4 r0 = st.rec0[kk[u]];
                         const float4 r1 = st.rec1[kk[u]];
-                        const float dx = subr(r0.x, pxf), dy = subr(r0.y, pyf);
-                        const float t4 = fmar(dx, mulr(dx, r1.x), mulr(dy, mulr(dy, r1.z)));
-                        const float power = subr(mulr(t4, -0.5f), mulr(dy, mulr(dx, r1.y)));
+                        // same expression trees as reference forward.cu:340-351 (see common.cuh)
+                        const float dx = r0.x - pxf, dy = r0.y - pyf;
+                        const float power = -0.5f * (r1.x * dx * dx + r1.z * dy * dy) - r1.y * dx * dy;
                         if (!(power > 0.0f)) {
-                            const float a = fminf(mulr(r1.w, expf(power)), 0.99f);
+                            const float a = fminf(0.99f, r1.w * expf(power));
                             if (!(a < 1.0f / 255.0f)) al[u] = a;
                         }
                     }
@@ -138,16 +138,16 @@ composite_fwd_kernel(int W, int H, int C, const uint2* __restrict__ ranges,
                     float wgt = 0.f;
                     float alpha = al[u];
                     if (!done && alpha > 0.f) {
-                        const float test_T = mulr(T, subr(1.0f, alpha));
+                        const float test_T = T * (1 - alpha);
                         if (test_T < 0.0001f) {
                             done = true;
                         } else {
-                            wgt = mulr(T, alpha);
                             const float4 r2 = st.rec2[kk[u]];
-                            Cr = fmar(T, mulr(alpha, r2.x), Cr);
-                            Cg = fmar(T, mulr(alpha, r2.y), Cg);
-                            Cb = fmar(T, mulr(alpha, r2.z), Cb);
-                            Dp = fmar(wgt, r2.w, Dp);
+                            Cr += r2.x * alpha * T;  // reference forward.cu:362-368
+                            Cg += r2.y * alpha * T;
+                            Cb += r2.z * alpha * T;
+                            wgt = alpha * T;
+                            Dp += r2.w * wgt;
                             T = test_T;
                             last_contrib = st.listpos[kk[u]];
                         }
@@ -207,9 +207,9 @@ composite_fwd_kernel(int W, int H, int C, const uint2* __restrict__ ranges,
         const size_t pix = (size_t)py * W + px;
         final_T[pix] = T;
         n_contrib[pix] = last_contrib;
-        out_color[pix] = fmar(T, bg[0], Cr);
-        out_color[HW + pix] = fmar(T, bg[1], Cg);
-        out_color[2 * HW + pix] = fmar(T, bg[2], Cb);
+        out_color[pix] = Cr + T * bg[0];  // reference forward.cu:389
+        out_color[HW + pix] = Cg + T * bg[1];
+        out_color[2 * HW + pix] = Cb + T * bg[2];
         out_depth[pix] = Dp;
     }
     if (CH > 0) {

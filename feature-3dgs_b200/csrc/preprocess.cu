@@ -27,157 +27,132 @@ __device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.8906114426405
 struct F3 {
     float x, y, z;
 };
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return F3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 operator*(float s, F3 a) { return F3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ F3 operator/(F3 a, float s) { return F3{a.x / s, a.y / s, a.z / s}; }
+
+// Column-major 3x3 (c[col][row]) with the same product expansion as the matrix library the
+// reference uses (GLM 0.9.9, type_mat3x3.inl:486-519): element (col j,row i) of A*B is
+// A[0][i]*B[j][0] + A[1][i]*B[j][1] + A[2][i]*B[j][2], summed left to right.  Keeping the same
+// expression tree (zero terms included) is what makes nvcc place the same FMAs as in the reference.
+struct M3 {
+    float c[3][3];
+};
+__device__ __forceinline__ M3 operator*(const M3& A, const M3& B) {
+    M3 R;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) R.c[j][i] = A.c[0][i] * B.c[j][0] + A.c[1][i] * B.c[j][1] + A.c[2][i] * B.c[j][2];
+    return R;
+}
+__device__ __forceinline__ M3 transpose(const M3& A) {
+    M3 R;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) R.c[j][i] = A.c[i][j];
+    return R;
+}
+__device__ __forceinline__ M3 cols(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1,
+                                   float c2) {
+    M3 R;
+    R.c[0][0] = a0; R.c[0][1] = a1; R.c[0][2] = a2;
+    R.c[1][0] = b0; R.c[1][1] = b1; R.c[1][2] = b2;
+    R.c[2][0] = c0; R.c[2][1] = c1; R.c[2][2] = c2;
+    return R;
+}
+
+// reference auxiliary.h:58-77: rows of the column-major 4x4 applied to a point
+__device__ __forceinline__ float xf(const float* __restrict__ m, int r, F3 p) {
+    return m[r] * p.x + m[4 + r] * p.y + m[8 + r] * p.z + m[12 + r];
+}
 
 // SH -> RGB, reference forward.cu:20-72.  `sh` points at this Gaussian's [M,3] coefficients.
-__device__ __forceinline__ F3 sh_to_rgb(int deg, const float* __restrict__ sh, float px, float py, float pz,
-                                        const float* __restrict__ cam, uint8_t& clamp_bits) {
-    const float dx = subr(px, cam[0]), dy = subr(py, cam[1]), dz = subr(pz, cam[2]);
-    const float len = sqrtr(dot3r(dx, dx, dy, dy, dz, dz));
-    const float x = divr(dx, len), y = divr(dy, len), z = divr(dz, len);
-    float res[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) res[c] = mulr(sh[c], kSH_C0);
+__device__ __forceinline__ F3 sh_to_rgb(int deg, const float* __restrict__ shp, F3 pos, const float* __restrict__ cam,
+                                        uint8_t& clamp_bits) {
+    const F3* sh = reinterpret_cast<const F3*>(shp);
+    F3 dir = pos - F3{cam[0], cam[1], cam[2]};
+    const F3 sq = F3{dir.x * dir.x, dir.y * dir.y, dir.z * dir.z};
+    dir = dir / sqrtf(sq.x + sq.y + sq.z);
+    F3 result = kSH_C0 * sh[0];
     if (deg > 0) {
-        const float ty = mulr(y, kSH_C1), tz = mulr(z, kSH_C1), tx = mulr(x, kSH_C1);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float r = subr(res[c], mulr(ty, sh[3 + c]));
-            r = fmar(tz, sh[6 + c], r);
-            res[c] = subr(r, mulr(tx, sh[9 + c]));
-        }
+        const float x = dir.x, y = dir.y, z = dir.z;
+        result = result - kSH_C1 * y * sh[1] + kSH_C1 * z * sh[2] - kSH_C1 * x * sh[3];
         if (deg > 1) {
-            const float xx = mulr(x, x), yy = mulr(y, y), zz = mulr(z, z);
-            const float xy = mulr(x, y), yz = mulr(y, z), xz = mulr(x, z);
-            const float zz2 = addr(zz, zz);
-            const float k4 = mulr(xy, kSH_C2[0]);
-            const float k5 = mulr(yz, kSH_C2[1]);
-            const float k6 = mulr(subr(subr(zz2, xx), yy), kSH_C2[2]);
-            const float k7 = mulr(xz, kSH_C2[3]);
-            const float xxmyy = subr(xx, yy);
-            const float k8 = mulr(xxmyy, kSH_C2[4]);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                float r = fmar(k4, sh[12 + c], res[c]);
-                r = fmar(k5, sh[15 + c], r);
-                r = fmar(k6, sh[18 + c], r);
-                r = fmar(k7, sh[21 + c], r);
-                res[c] = fmar(k8, sh[24 + c], r);
-            }
+            const float xx = x * x, yy = y * y, zz = z * z;
+            const float xy = x * y, yz = y * z, xz = x * z;
+            result = result + kSH_C2[0] * xy * sh[4] + kSH_C2[1] * yz * sh[5] +
+                     kSH_C2[2] * (2.0f * zz - xx - yy) * sh[6] + kSH_C2[3] * xz * sh[7] +
+                     kSH_C2[4] * (xx - yy) * sh[8];
             if (deg > 2) {
-                const float xx3 = mulr(xx, 3.0f), yy3 = mulr(yy, 3.0f);
-                const float k9 = mulr(mulr(y, kSH_C3[0]), subr(xx3, yy));
-                const float k10 = mulr(z, mulr(xy, kSH_C3[1]));
-                const float q = subr(subr(mulr(zz, 4.0f), xx), yy);
-                const float k11 = mulr(mulr(y, kSH_C3[2]), q);
-                const float k12 = mulr(mulr(z, kSH_C3[3]), subr(subr(zz2, xx3), yy3));
-                const float k13 = mulr(mulr(x, kSH_C3[4]), q);
-                const float k14 = mulr(mulr(z, kSH_C3[5]), xxmyy);
-                const float k15 = mulr(mulr(x, kSH_C3[6]), subr(xx, yy3));
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    float r = fmar(k9, sh[27 + c], res[c]);
-                    r = fmar(k10, sh[30 + c], r);
-                    r = fmar(k11, sh[33 + c], r);
-                    r = fmar(k12, sh[36 + c], r);
-                    r = fmar(k13, sh[39 + c], r);
-                    r = fmar(k14, sh[42 + c], r);
-                    res[c] = fmar(k15, sh[45 + c], r);
-                }
+                result = result + kSH_C3[0] * y * (3.0f * xx - yy) * sh[9] + kSH_C3[1] * xy * z * sh[10] +
+                         kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[11] +
+                         kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12] +
+                         kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[13] + kSH_C3[5] * z * (xx - yy) * sh[14] +
+                         kSH_C3[6] * x * (xx - 3.0f * yy) * sh[15];
             }
         }
     }
-    F3 out;
-    clamp_bits = 0;
-    float v;
-    v = addr(res[0], 0.5f);
-    if (v < 0.f) { clamp_bits |= 1; v = 0.f; }
-    out.x = v;
-    v = addr(res[1], 0.5f);
-    if (v < 0.f) { clamp_bits |= 2; v = 0.f; }
-    out.y = v;
-    v = addr(res[2], 0.5f);
-    if (v < 0.f) { clamp_bits |= 4; v = 0.f; }
-    out.z = v;
-    return out;
+    result.x += 0.5f;
+    result.y += 0.5f;
+    result.z += 0.5f;
+    clamp_bits = (result.x < 0 ? 1 : 0) | (result.y < 0 ? 2 : 0) | (result.z < 0 ? 4 : 0);
+    return F3{fmaxf(result.x, 0.0f), fmaxf(result.y, 0.0f), fmaxf(result.z, 0.0f)};
 }
 
 // scale/rotation -> world covariance (upper triangle), reference forward.cu:119-153
 __device__ __forceinline__ void cov3d_from_scale_rot(const float* __restrict__ s3, float mod,
                                                      const float* __restrict__ q4, float* cov) {
-    const float sx = mulr(mod, s3[0]), sy = mulr(mod, s3[1]), sz = mulr(mod, s3[2]);
-    const float r = q4[0], x = q4[1], y = q4[2], z = q4[3];
-    const float yy = mulr(y, y), zz = mulr(z, z);
-    const float xy = mulr(x, y), rz = mulr(r, z), xz = mulr(x, z), ry = mulr(r, y);
-    const float yz = mulr(y, z), rx = mulr(r, x);
-    const float a = addr(yy, zz);
-    const float b = fmar(x, x, zz);
-    const float c = fmar(x, x, yy);
-    const float R00 = subr(1.0f, addr(a, a));
-    const float R11 = subr(1.0f, addr(b, b));
-    const float R22 = subr(1.0f, addr(c, c));
-    float t;
-    // columns of M = S * R (GLM column-major)
-    const float m00 = mulr(sx, R00);
-    t = subr(xy, rz); const float m01 = mulr(sy, addr(t, t));
-    t = addr(ry, xz); const float m02 = mulr(sz, addr(t, t));
-    t = addr(xy, rz); const float m10 = mulr(sx, addr(t, t));
-    const float m11 = mulr(sy, R11);
-    t = subr(yz, rx); const float m12 = mulr(sz, addr(t, t));
-    t = subr(xz, ry); const float m20 = mulr(sx, addr(t, t));
-    t = addr(rx, yz); const float m21 = mulr(sy, addr(t, t));
-    const float m22 = mulr(sz, R22);
-    cov[0] = dot3r(m00, m00, m01, m01, m02, m02);
-    cov[1] = dot3r(m10, m00, m11, m01, m12, m02);
-    cov[2] = dot3r(m20, m00, m21, m01, m22, m02);
-    cov[3] = dot3r(m10, m10, m11, m11, m12, m12);
-    cov[4] = dot3r(m20, m10, m21, m11, m22, m12);
-    cov[5] = dot3r(m20, m20, m21, m21, m22, m22);
+    M3 S = cols(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
+    S.c[0][0] = mod * s3[0];
+    S.c[1][1] = mod * s3[1];
+    S.c[2][2] = mod * s3[2];
+    const float r = q4[0], x = q4[1], y = q4[2], z = q4[3];  // not renormalised (forward.cu:128)
+    const M3 R = cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                      2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                      2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    const M3 M = S * R;
+    const M3 Sigma = transpose(M) * M;
+    cov[0] = Sigma.c[0][0];
+    cov[1] = Sigma.c[0][1];
+    cov[2] = Sigma.c[0][2];
+    cov[3] = Sigma.c[1][1];
+    cov[4] = Sigma.c[1][2];
+    cov[5] = Sigma.c[2][2];
 }
 
 // EWA projection of the 3-D covariance, reference forward.cu:75-114.  Returns (a, b, c) with the
 // 0.3 dilation applied.  Also hands back the intermediates the backward needs.
 struct Cov2D {
     float a, b, c;
-    float T00, T01, T02, T10, T11, T12;  // upper two rows of T = W * J
+    float T00, T01, T02, T10, T11, T12;  // T[0][*], T[1][*] of T = W * J (column-major indexing)
     float tx, ty, tz;                    // clamped view-space mean
     float txtz, tytz;                    // unclamped ratios
 };
-__device__ __forceinline__ Cov2D project_cov(float px, float py, float pz, const float* __restrict__ vm,
-                                             float focal_x, float focal_y, float tan_fovx, float tan_fovy,
-                                             const float* __restrict__ cv) {
+__device__ __forceinline__ Cov2D project_cov(F3 mean, const float* __restrict__ vm, float focal_x, float focal_y,
+                                             float tan_fovx, float tan_fovy, const float* __restrict__ cv) {
     Cov2D o;
-    const float tx = xform_row(vm, 0, px, py, pz);
-    const float ty = xform_row(vm, 1, px, py, pz);
-    const float tz = xform_row(vm, 2, px, py, pz);
-    const float limx = mulr(tan_fovx, 1.3f), limy = mulr(tan_fovy, 1.3f);
-    o.txtz = divr(tx, tz);
-    o.tytz = divr(ty, tz);
-    const float cx = fminf(limx, fmaxf(-limx, o.txtz));
-    const float cy = fminf(limy, fmaxf(-limy, o.tytz));
-    const float ntz = -tz;
-    const float tz2 = mulr(tz, tz);
-    const float J00 = divr(focal_x, tz);
-    const float J02 = divr(mulr(focal_x, mulr(cx, ntz)), tz2);
-    const float J11 = divr(focal_y, tz);
-    const float J12 = divr(mulr(focal_y, mulr(cy, ntz)), tz2);
-    o.tx = mulr(cx, tz);
-    o.ty = mulr(cy, tz);
-    o.tz = tz;
-    o.T00 = fmar(vm[2], J02, mulr(vm[0], J00));
-    o.T01 = fmar(vm[6], J02, mulr(vm[4], J00));
-    o.T02 = fmar(J02, vm[10], mulr(vm[8], J00));
-    o.T10 = fmar(vm[2], J12, mulr(J11, vm[1]));
-    o.T11 = fmar(vm[6], J12, mulr(J11, vm[5]));
-    o.T12 = fmar(J12, vm[10], mulr(J11, vm[9]));
-    const float A00 = dot3r(o.T00, cv[0], o.T01, cv[1], o.T02, cv[2]);
-    const float A10 = dot3r(o.T10, cv[0], o.T11, cv[1], o.T12, cv[2]);
-    const float A01 = dot3r(o.T00, cv[1], o.T01, cv[3], o.T02, cv[4]);
-    const float A11 = dot3r(o.T10, cv[1], o.T11, cv[3], o.T12, cv[4]);
-    const float A02 = dot3r(o.T00, cv[2], o.T01, cv[4], o.T02, cv[5]);
-    const float A12 = dot3r(o.T10, cv[2], o.T11, cv[4], o.T12, cv[5]);
-    o.a = addr(dot3r(o.T00, A00, o.T01, A01, o.T02, A02), 0.3f);
-    o.b = dot3r(o.T00, A10, o.T01, A11, o.T02, A12);
-    o.c = addr(dot3r(o.T10, A10, o.T11, A11, o.T12, A12), 0.3f);
+    F3 t = F3{xf(vm, 0, mean), xf(vm, 1, mean), xf(vm, 2, mean)};
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    const M3 J = cols(focal_x / t.z, 0.0f, -(focal_x * t.x) / (t.z * t.z), 0.0f, focal_y / t.z,
+                      -(focal_y * t.y) / (t.z * t.z), 0.0f, 0.0f, 0.0f);
+    const M3 Wm = cols(vm[0], vm[4], vm[8], vm[1], vm[5], vm[9], vm[2], vm[6], vm[10]);
+    const M3 T = Wm * J;
+    const M3 Vrk = cols(cv[0], cv[1], cv[2], cv[1], cv[3], cv[4], cv[2], cv[4], cv[5]);
+    M3 cov = transpose(T) * transpose(Vrk) * T;
+    cov.c[0][0] += 0.3f;
+    cov.c[1][1] += 0.3f;
+    o.a = cov.c[0][0]; o.b = cov.c[0][1]; o.c = cov.c[1][1];
+    o.T00 = T.c[0][0]; o.T01 = T.c[0][1]; o.T02 = T.c[0][2];
+    o.T10 = T.c[1][0]; o.T11 = T.c[1][1]; o.T12 = T.c[1][2];
+    o.tx = t.x; o.ty = t.y; o.tz = t.z; o.txtz = txtz; o.tytz = tytz;
     return o;
 }
 
@@ -212,10 +187,10 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
     int my_radii = 0;
     uint32_t my_tiles = 0;
     do {
-        const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+        const F3 p_orig = F3{means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
         const float* vm = vp.viewmatrix;
         const float* pm = vp.projmatrix;
-        const float depth = xform_row(vm, 2, px, py, pz);
+        const float depth = xf(vm, 2, p_orig);
         if (depth <= 0.2f) {  // reference auxiliary.h:160 (only the near plane culls)
             if (prefiltered) {
                 printf("Point is filtered although prefiltered is set. This shouldn't happen!");
@@ -223,11 +198,9 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
             }
             break;
         }
-        const float hx = xform_row(pm, 0, px, py, pz);
-        const float hy = xform_row(pm, 1, px, py, pz);
-        const float hw = xform_row(pm, 3, px, py, pz);
-        const float p_w = rcpr(addr(hw, 0.0000001f));
-        const float projx = mulr(hx, p_w), projy = mulr(hy, p_w);
+        const float hx = xf(pm, 0, p_orig), hy = xf(pm, 1, p_orig), hw = xf(pm, 3, p_orig);
+        const float p_w = 1.0f / (hw + 0.0000001f);
+        const float projx = hx * p_w, projy = hy * p_w;
 
         float cv[6];
         if (cov3D_precomp != nullptr) {
@@ -238,15 +211,15 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
 #pragma unroll
             for (int i = 0; i < 6; i++) cov3D[6 * idx + i] = cv[i];
         }
-        const Cov2D c2 = project_cov(px, py, pz, vm, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cv);
-        const float det = subr(mulr(c2.a, c2.c), mulr(c2.b, c2.b));
+        const Cov2D c2 = project_cov(p_orig, vm, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cv);
+        const float det = (c2.a * c2.c - c2.b * c2.b);
         if (det == 0.0f) break;
-        const float det_inv = rcpr(det);
-        const float conA = mulr(c2.c, det_inv), conB = mulr(det_inv, -c2.b), conC = mulr(c2.a, det_inv);
-        const float mid = mulr(addr(c2.a, c2.c), 0.5f);
-        const float sq = sqrtr(fmaxf(subr(mulr(mid, mid), det), 0.1f));
-        const float lam = fmaxf(addr(mid, sq), subr(mid, sq));
-        const float rad_f = ceilf(mulr(sqrtr(lam), 3.0f));
+        const float det_inv = 1.f / det;
+        const float conA = c2.c * det_inv, conB = -c2.b * det_inv, conC = c2.a * det_inv;
+        const float mid = 0.5f * (c2.a + c2.c);
+        const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float rad_f = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
         const int rad = (int)rad_f;
         const float ix = ndc2pix(projx, vp.W), iy = ndc2pix(projy, vp.H);
         uint32_t x0, y0, x1, y1;
@@ -257,7 +230,7 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
         SplatRec r;
         uint8_t cb = 0;
         if (colors_precomp == nullptr) {
-            F3 col = sh_to_rgb(vp.D, shs + (size_t)idx * vp.M * 3, px, py, pz, vp.cam_pos, cb);
+            F3 col = sh_to_rgb(vp.D, shs + (size_t)idx * vp.M * 3, p_orig, vp.cam_pos, cb);
             r.r = col.x; r.g = col.y; r.b = col.z;
         } else {
             r.r = colors_precomp[3 * idx]; r.g = colors_precomp[3 * idx + 1]; r.b = colors_precomp[3 * idx + 2];
@@ -267,7 +240,11 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
         r.ca = conA; r.cb = conB; r.cc = conC;
         r.op = opacities[idx];
         r.depth = depth;
+#ifdef F3DGS_SASS_AUDIT  // build used only to compare the FP instruction mix with the reference kernel
+        r.ex = r.ey = 0.f;
+#else
         alpha_extent(conA, conB, conC, r.op, r.ex, r.ey);
+#endif
         float4* dst = reinterpret_cast<float4*>(rec + idx);
         dst[0] = make_float4(r.x, r.y, r.ex, r.ey);
         dst[1] = make_float4(r.ca, r.cb, r.cc, r.op);
@@ -284,7 +261,7 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
                     uint8_t* __restrict__ present) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
-    const float z = xform_row(vm, 2, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float z = xf(vm, 2, F3{means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]});
     present[idx] = z > 0.2f ? 1 : 0;
 }
 
@@ -318,7 +295,7 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
     float cv[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) cv[i] = cov3D[6 * idx + i];
-    const Cov2D c2 = project_cov(mx, my, mz, vm, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cv);
+    const Cov2D c2 = project_cov(F3{mx, my, mz}, vm, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cv);
     const float limx = 1.3f * vp.tan_fovx, limy = 1.3f * vp.tan_fovy;
     const float x_grad_mul = (c2.txtz < -limx || c2.txtz > limx) ? 0.f : 1.f;
     const float y_grad_mul = (c2.tytz < -limy || c2.tytz > limy) ? 0.f : 1.f;

@@ -11,9 +11,10 @@
  * itself (oracle/_ref, built from the unmodified sources by oracle/build_ref.py and run on the
  * B200 by oracle/make_golden.py); the vectors are committed under tests/golden/.
  *
- * Numerics: the forward per-Gaussian stage reproduces the exact fp32 operation sequence nvcc
- * emits for the reference (FMA placement read off its PTX; fmaf() here, -ffp-contract=off), so
- * radii / tile rectangles / depth keys / point_list / ranges are bit-identical to the GPU.
+ * Numerics: the forward per-Gaussian stage reproduces the exact fp32 operation sequence of the
+ * reference's sm_100a build (FMA placement read off its PTX *and* SASS -- ptxas fuses further
+ * mul/add pairs the PTX still shows separately; fmaf() here, -ffp-contract=off), so radii / tile
+ * rectangles / depth keys / point_list / ranges are bit-identical to the GPU.
  * expf() comes from libm and differs from CUDA's by <= 2 ulp, so images agree to ~1e-6 and
  * n_contrib can differ on measure-zero threshold ties.
  *
@@ -70,9 +71,9 @@ static void sh_to_rgb(int deg, const float* sh, const float* p, const float* cam
     if (deg > 0) {
         const float ty = y * SH_C1, tz = z * SH_C1, tx = x * SH_C1;
         for (int c = 0; c < 3; c++) {
-            float r = res[c] - ty * sh[3 + c];
+            float r = fmaf(-ty, sh[3 + c], res[c]); /* ptxas fuses res - ty*sh (SASS: FFMA -R, R, R) */
             r = fmaf(tz, sh[6 + c], r);
-            res[c] = r - tx * sh[9 + c];
+            res[c] = fmaf(-tx, sh[9 + c], r);
         }
         if (deg > 1) {
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
@@ -87,15 +88,15 @@ static void sh_to_rgb(int deg, const float* sh, const float* p, const float* cam
                 res[c] = fmaf(k8, sh[24 + c], r);
             }
             if (deg > 2) {
-                const float xx3 = xx * 3.0f, yy3 = yy * 3.0f;
-                const float k9 = (y * SH_C3[0]) * (xx3 - yy);
+                /* SASS: the x3 / x4 products are fused into the subtractions that consume them */
+                const float k9 = (y * SH_C3[0]) * fmaf(xx, 3.0f, -yy);
                 const float k10 = z * (xy * SH_C3[1]);
-                const float q = ((zz * 4.0f) - xx) - yy;
+                const float q = fmaf(zz, 4.0f, -xx) - yy;
                 const float k11 = (y * SH_C3[2]) * q;
-                const float k12 = (z * SH_C3[3]) * ((zz2 - xx3) - yy3);
+                const float k12 = (z * SH_C3[3]) * fmaf(yy, -3.0f, fmaf(xx, -3.0f, zz2));
                 const float k13 = (x * SH_C3[4]) * q;
                 const float k14 = (z * SH_C3[5]) * xxmyy;
-                const float k15 = (x * SH_C3[6]) * (xx - yy3);
+                const float k15 = (x * SH_C3[6]) * fmaf(yy, -3.0f, xx);
                 for (int c = 0; c < 3; c++) {
                     float r = fmaf(k9, sh[27 + c], res[c]);
                     r = fmaf(k10, sh[30 + c], r);
@@ -119,18 +120,20 @@ static void sh_to_rgb(int deg, const float* sh, const float* p, const float* cam
 static void cov3d_from_scale_rot(const float* s3, float mod, const float* q4, float* cov) {
     const float sx = mod * s3[0], sy = mod * s3[1], sz = mod * s3[2];
     const float r = q4[0], x = q4[1], y = q4[2], z = q4[3];
-    const float yy = y * y, zz = z * z, xy = x * y, rz = r * z, xz = x * z, ry = r * y, yz = y * z, rx = r * x;
+    /* SASS of the reference build: of each product pair (xy,rz) (xz,ry) (yz,rx) ptxas keeps one product as a
+     * rounded FMUL and fuses the other into both the sum and the difference */
+    const float yy = y * y, zz = z * z, rz = r * z, xz = x * z, rx = r * x;
     const float a = yy + zz, b = fmaf(x, x, zz), c = fmaf(x, x, yy);
     const float R00 = 1.0f - (a + a), R11 = 1.0f - (b + b), R22 = 1.0f - (c + c);
     float t;
     const float m00 = sx * R00;
-    t = xy - rz; const float m01 = sy * (t + t);
-    t = ry + xz; const float m02 = sz * (t + t);
-    t = xy + rz; const float m10 = sx * (t + t);
+    t = fmaf(x, y, -rz); const float m01 = sy * (t + t);  /* 2(xy - rz) */
+    t = fmaf(r, y, xz);  const float m02 = sz * (t + t);  /* 2(xz + ry) */
+    t = fmaf(x, y, rz);  const float m10 = sx * (t + t);  /* 2(xy + rz) */
     const float m11 = sy * R11;
-    t = yz - rx; const float m12 = sz * (t + t);
-    t = xz - ry; const float m20 = sx * (t + t);
-    t = rx + yz; const float m21 = sy * (t + t);
+    t = fmaf(y, z, -rx); const float m12 = sz * (t + t);  /* 2(yz - rx) */
+    t = fmaf(-r, y, xz); const float m20 = sx * (t + t);  /* 2(xz - ry) */
+    t = fmaf(y, z, rx);  const float m21 = sy * (t + t);  /* 2(yz + rx) */
     const float m22 = sz * R22;
     cov[0] = dot3r(m00, m00, m01, m01, m02, m02);
     cov[1] = dot3r(m10, m00, m11, m01, m12, m02);
@@ -218,12 +221,12 @@ long long oracle_preprocess(int P, int D, int M, const float* means3D, const flo
             cv = cvbuf;
         }
         const cov2d_t c2 = project_cov(p, viewmatrix, focal_x, focal_y, tan_fovx, tan_fovy, cv);
-        const float det = c2.a * c2.c - c2.b * c2.b; /* mul, mul, sub: not contracted in the reference */
+        const float det = fmaf(c2.a, c2.c, -(c2.b * c2.b)); /* SASS: FMUL b*b; FFMA a, c, -bb */
         if (det == 0.0f) continue;
         const float det_inv = 1.0f / det;
         const float conA = c2.c * det_inv, conB = det_inv * -c2.b, conC = c2.a * det_inv;
         const float mid = (c2.a + c2.c) * 0.5f;
-        const float sq = sqrtf(fmaxf(mid * mid - det, 0.1f));
+        const float sq = sqrtf(fmaxf(fmaf(mid, mid, -det), 0.1f)); /* SASS: FFMA mid, mid, -det */
         const float lam = fmaxf(mid + sq, mid - sq);
         const float rad_f = ceilf(sqrtf(lam) * 3.0f);
         const int rad = (int)rad_f;
@@ -348,7 +351,7 @@ void oracle_render(int W, int H, int C, const uint32_t* ranges, const uint32_t* 
                         const float dx = means2D[2 * g] - pxf, dy = means2D[2 * g + 1] - pyf;
                         const float* co = conic_opacity + 4 * g;
                         const float t4 = fmaf(dx, dx * co[0], dy * (dy * co[2]));
-                        const float power = (t4 * -0.5f) - dy * (dx * co[1]);
+                        const float power = fmaf(t4, -0.5f, -(dy * (dx * co[1]))); /* SASS: FFMA t4, -0.5, -R */
                         if (power > 0.0f) continue;
                         const float alpha = fminf(co[3] * expf(power), 0.99f);
                         if (alpha < 1.0f / 255.0f) continue;
@@ -434,7 +437,7 @@ void oracle_render_backward(int W, int H, int C, const uint32_t* ranges, const u
                         const float dx = means2D[2 * g] - pxf, dy = means2D[2 * g + 1] - pyf;
                         const float* co = conic_opacity + 4 * g;
                         const float t4 = fmaf(dx, dx * co[0], dy * (dy * co[2]));
-                        const float power = (t4 * -0.5f) - dy * (dx * co[1]);
+                        const float power = fmaf(t4, -0.5f, -(dy * (dx * co[1]))); /* SASS: FFMA t4, -0.5, -R */
                         if (power > 0.0f) continue;
                         const float G = expf(power);
                         const float alpha = fminf(co[3] * G, 0.99f);
