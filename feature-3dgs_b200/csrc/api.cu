@@ -10,7 +10,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/f3dgs_b200.h"
 #include "kernels.h"
@@ -30,6 +32,46 @@ int fail(int code, const std::string& msg) {
 }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- optional per-stage timing with CUDA events on the launch stream
+struct StageRec {
+    int stage;
+    cudaEvent_t e0, e1;
+};
+bool g_profile = false;
+std::mutex g_profile_mu;
+std::vector<StageRec> g_recs;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {
+    bool on;
+    StageRec r;
+    cudaStream_t s;
+    StageTimer(int stage, cudaStream_t stream) : on(g_profile), s(stream) {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_profile_mu);
+        r.stage = stage;
+        r.e0 = get_event();
+        r.e1 = get_event();
+        cudaEventRecord(r.e0, s);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(r.e1, s);
+        std::lock_guard<std::mutex> lk(g_profile_mu);
+        g_recs.push_back(r);
+    }
+};
 
 struct GeomLayout {
     size_t rec, cov3d, clamped, tiles, offsets, radii, fixed_bytes;
@@ -114,6 +156,30 @@ int f3dgs_abi_version(void) { return F3DGS_ABI_VERSION; }
 const char* f3dgs_last_error(void) { return t_error.c_str(); }
 unsigned long long f3dgs_launch_count(void) { return g_launches; }
 
+void f3dgs_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    g_profile = on != 0;
+}
+
+int f3dgs_profile_read(double* ms, unsigned long long* count) {
+    if (!ms || !count) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_profile_read: NULL output");
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    for (const StageRec& r : g_recs) {
+        float t = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.e0, r.e1);
+        if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("profile_read: ") + cudaGetErrorString(e));
+        if (r.stage >= 0 && r.stage < F3DGS_N_STAGES) {
+            ms[r.stage] += t;
+            count[r.stage] += 1;
+        }
+        g_event_pool.push_back(r.e0);
+        g_event_pool.push_back(r.e1);
+    }
+    g_recs.clear();
+    return 0;
+}
+
 int f3dgs_get_layout(int P, int width, int height, int R, f3dgs_layout* out) {
     if (!out || P < 0 || width <= 0 || height <= 0 || R < 0)
         return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_get_layout: bad argument");
@@ -184,12 +250,16 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     uint32_t* n_contrib = reinterpret_cast<uint32_t*>(img + il.n_contrib);
     uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
 
-    launch_preprocess_fwd(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
-                          prefiltered != 0, radii, rec, cov3d, clamped, tiles_touched, stream);
+    {
+        StageTimer t(F3DGS_STAGE_PREPROCESS_FWD, stream);
+        launch_preprocess_fwd(vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                              prefiltered != 0, radii, rec, cov3d, clamped, tiles_touched, stream);
+    }
     STAGE_CHECK("preprocess");
-
-    CUDA_TRY(cub::DeviceScan::InclusiveSum(geom + gl.fixed_bytes, scan_bytes, tiles_touched, offsets, P, stream));
-    g_launches += 2;
+    {
+        StageTimer t(F3DGS_STAGE_SCAN, stream);
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(geom + gl.fixed_bytes, scan_bytes, tiles_touched, offsets, P, stream));
+    }
     STAGE_CHECK("scan");
 
     static thread_local int* h_count = nullptr;
@@ -214,19 +284,31 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
 
     CUDA_TRY(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), stream));
     if (R > 0) {
-        launch_duplicate_keys(P, rec, offsets, radii, vp.grid_x, vp.grid_y, keys_unsorted, point_list_unsorted,
-                              stream);
+        {
+            StageTimer t(F3DGS_STAGE_DUPLICATE_KEYS, stream);
+            launch_duplicate_keys(P, rec, offsets, radii, vp.grid_x, vp.grid_y, keys_unsorted, point_list_unsorted,
+                                  stream);
+        }
         STAGE_CHECK("duplicate_keys");
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin + bl.fixed_bytes, sort_bytes, keys_unsorted, keys,
-                                                 point_list_unsorted, point_list, R, 0, end_bit, stream));
-        g_launches += (unsigned long long)((end_bit + 7) / 8 + 2);
+        {
+            StageTimer t(F3DGS_STAGE_SORT, stream);
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin + bl.fixed_bytes, sort_bytes, keys_unsorted, keys,
+                                                     point_list_unsorted, point_list, R, 0, end_bit, stream));
+        }
         STAGE_CHECK("sort");
-        launch_tile_ranges(R, keys, ranges, stream);
+        {
+            StageTimer t(F3DGS_STAGE_TILE_RANGES, stream);
+            launch_tile_ranges(R, keys, ranges, stream);
+        }
         STAGE_CHECK("tile_ranges");
     }
 
-    cudaError_t e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T,
-                                         n_contrib, out_color, out_feature_map, out_depth, stream);
+    cudaError_t e;
+    {
+        StageTimer t(F3DGS_STAGE_COMPOSITE_FWD, stream);
+        e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
+                                 out_color, out_feature_map, out_depth, stream);
+    }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_fwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_fwd");
     return R;
@@ -273,14 +355,20 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
     const uint2* ranges = reinterpret_cast<const uint2*>(image_buffer + il.ranges);
     const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list);
 
-    cudaError_t e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,
-                                         dL_dfeaturepix, dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
-                                         dL_dsemantic_feature, dL_dz, stream);
+    cudaError_t e;
+    {
+        StageTimer t(F3DGS_STAGE_COMPOSITE_BWD, stream);
+        e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, dL_dfeaturepix,
+                                 dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dsemantic_feature, dL_dz,
+                                 stream);
+    }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_bwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_bwd");
-
-    launch_preprocess_bwd(vp, means3D, radii, shs, clamped, scales, rotations, cov3d, dL_dmean2D, dL_dconic,
-                          dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, stream);
+    {
+        StageTimer t(F3DGS_STAGE_PREPROCESS_BWD, stream);
+        launch_preprocess_bwd(vp, means3D, radii, shs, clamped, scales, rotations, cov3d, dL_dmean2D, dL_dconic,
+                              dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, stream);
+    }
     STAGE_CHECK("preprocess_bwd");
     return 0;
 }

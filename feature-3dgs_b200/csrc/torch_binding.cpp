@@ -17,6 +17,7 @@
 
 #include <string>
 #include <tuple>
+#include <vector>
 
 #include "../../include/f3dgs_b200.h"
 
@@ -216,4 +217,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("debug_views", &debugViews);
     m.def("launch_count", []() { return (unsigned long long)f3dgs_launch_count(); });
     m.def("abi_version", []() { return f3dgs_abi_version(); });
+    m.def("profile_enable", [](bool on) { f3dgs_profile_enable(on ? 1 : 0); });
+    m.def("profile_read", []() {
+        std::vector<double> ms(F3DGS_N_STAGES, 0.0);
+        std::vector<unsigned long long> cnt(F3DGS_N_STAGES, 0);
+        check_rc(f3dgs_profile_read(ms.data(), cnt.data()), "f3dgs_profile_read");
+        return std::make_pair(ms, cnt);
+    });
 }

@@ -132,8 +132,26 @@ typedef struct f3dgs_layout {
 
 int f3dgs_get_layout(int P, int width, int height, int R, f3dgs_layout* out);
 
-/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+/* Number of this library's own kernels launched in this process (CUB's scan/sort kernels are not
+ * counted) -- bench.py reports the delta over its timed region as gpu_launches. */
 unsigned long long f3dgs_launch_count(void);
+
+/* ---- per-stage device timing (bench.py roofline) ---------------------------------------------
+ * When enabled, every stage is bracketed by CUDA events on the launch stream (no host sync).
+ * f3dgs_profile_read synchronises the recorded events, adds the elapsed milliseconds and launch
+ * counts per stage into ms[F3DGS_N_STAGES] / count[F3DGS_N_STAGES] and clears the recordings.
+ * Stage ids: */
+#define F3DGS_STAGE_PREPROCESS_FWD 0
+#define F3DGS_STAGE_SCAN 1
+#define F3DGS_STAGE_DUPLICATE_KEYS 2
+#define F3DGS_STAGE_SORT 3
+#define F3DGS_STAGE_TILE_RANGES 4
+#define F3DGS_STAGE_COMPOSITE_FWD 5
+#define F3DGS_STAGE_COMPOSITE_BWD 6
+#define F3DGS_STAGE_PREPROCESS_BWD 7
+#define F3DGS_N_STAGES 8
+void f3dgs_profile_enable(int on);
+int f3dgs_profile_read(double* ms, unsigned long long* count);
 
 /* Last error message of the calling thread ("" if none). */
 const char* f3dgs_last_error(void);
