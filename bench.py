@@ -279,6 +279,8 @@ def main():
 
     # ---------------- timed region 1: device-resident `value`
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()  # nvidia-smi takes ~1 s to produce its first row: start before the warm-up
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -286,11 +288,7 @@ def main():
         _C.profile_read()
         _C.profile_enable(True)
         launches0 = _C.launch_count()
-    if sampler:
-        sampler.start()
     ms_total = timed(step_device, args.steps, 0)
-    if sampler:
-        clocks = sampler.stop()
     if _C is not None:
         launches = _C.launch_count() - launches0
         _C.profile_enable(False)
@@ -301,6 +299,8 @@ def main():
     # ---------------- timed region 2: end to end
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     e2e_value = views_per_step * args.steps / (ms_e2e / 1000.0)
+    if sampler:
+        clocks = sampler.stop()  # rows cover warm-up + both timed regions (the GPU is busy throughout)
 
     if rank != 0:
         if distributed:

@@ -87,12 +87,13 @@ struct GeomLayout {
     }
 };
 struct ImgLayout {
-    size_t final_T, n_contrib, ranges, bytes;
+    size_t final_T, n_contrib, ranges, counters, bytes;
     ImgLayout(size_t HW, size_t tiles) {
         size_t o = 0;
         final_T = o;    o = align_up(o + HW * 4);
         n_contrib = o;  o = align_up(o + HW * 4);
         ranges = o;     o = align_up(o + tiles * 8);
+        counters = o;   o = align_up(o + 256);  // tile work counters of the persistent composite kernels
         bytes = o;
     }
 };
@@ -307,7 +308,8 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     {
         StageTimer t(F3DGS_STAGE_COMPOSITE_FWD, stream);
         e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
-                                 out_color, out_feature_map, out_depth, stream);
+                                 out_color, out_feature_map, out_depth, reinterpret_cast<int*>(img + il.counters),
+                                 stream);
     }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_fwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_fwd");
@@ -360,7 +362,7 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
         StageTimer t(F3DGS_STAGE_COMPOSITE_BWD, stream);
         e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, dL_dfeaturepix,
                                  dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dsemantic_feature, dL_dz,
-                                 stream);
+                                 reinterpret_cast<int*>(image_buffer + il.counters) + 16, stream);
     }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_bwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_bwd");

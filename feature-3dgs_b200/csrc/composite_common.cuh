@@ -1,24 +1,44 @@
-// Shared machinery of the forward and backward composite kernels.
+// Shared machinery of the forward and backward composite kernels (persistent, warp-specialised).
 //
-// One CTA renders one 16x16 tile (reference: one 256-thread block per tile, forward.cu:261-396).
-// Here the CTA is 9 warps:
-//   warps 0..7  consumers; warp w owns the 8x4 pixel block (w&1, w>>1) of the tile, one pixel
-//               per lane in the alpha pass, one float4 of channels per lane in the feature pass
-//   warp  8     producer: walks the tile's slice of the depth-sorted instance list, drops the
-//               instances whose alpha>=1/255 footprint cannot reach the tile, and fills a ring of
-//               shared-memory stages: the 48-byte splat records with 128-bit loads, the C-wide
-//               feature rows with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) that
-//               complete on the stage's "full" mbarrier.
-// Consumers release a stage through its "empty" mbarrier; no __syncthreads in the main loop, so
-// the 8 pixel blocks drift apart freely (a block whose pixels are all saturated stops early).
+// The reference renders one 16x16 tile per 256-thread block, every thread doing everything
+// (forward.cu:261-396).  Here a persistent CTA (one per SM) pulls tiles from an atomic counter and
+// splits the work over three warp roles that talk only through shared-memory rings + mbarriers:
+//
+//   producer (1 warp)     walks the tile's slice of the depth-sorted instance list, drops the
+//                         instances whose alpha >= 1/255 footprint cannot reach the tile, and fills
+//                         a ring of stages: 48-byte splat records via 128-bit loads, C-wide feature
+//                         rows via 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) that complete on
+//                         the stage's `full` mbarrier.  It runs ahead across tile boundaries, so
+//                         the next tile's first stage is already resident when the consumers get
+//                         there (no per-tile start-up bubble).
+//   alpha warps (4)       warp a owns the two horizontally adjacent 8x4 pixel blocks 2a, 2a+1 of the
+//                         tile, one pixel of each per lane: alpha, the T recurrence, RGB/depth (and in
+//                         the backward every geometric gradient term).  They publish the blend weights
+//                         w = alpha*T as a [instance][pixel] tile plus a per-instance pixel mask in a
+//                         small per-block ring (`wfull`/`wempty`).
+//   feature warps (8)     warp b consumes block b's weight tiles with one float4 of channels per
+//                         lane: all 32 pixels x 4 channels of the block stay in registers; weights
+//                         arrive as broadcast LDS.128 per 2x2 pixel quad and feed 16 FFMAs.
+//
+// 16 warps = 512 threads are launched with 128 registers each (the whole 64K register file);
+// setmaxnreg then moves registers between the warpgroups: producer group 40, alpha group 104,
+// the two feature groups 184 per thread (5120 + 13312 + 47104 = 65536).
 #pragma once
 #include "kernels.h"
 
 namespace f3dgs {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kBlockThreads = (kConsumerWarps + 1) * 32;
+constexpr int kBlocksPerTile = 8;   // 8x4-pixel blocks in a 16x16 tile
+constexpr int kProducerWarp = 0;    // warps 0..3: producer warpgroup (warps 1..3 retire at once)
+constexpr int kAlphaWarp0 = 4;      // warps 4..7, two pixel blocks each
+constexpr int kAlphaWarps = 4;
+constexpr int kFeatWarp0 = 8;       // warps 8..15, one pixel block each
+constexpr int kThreadsV2 = 16 * 32;
 constexpr int kStageEntries = 32;
+constexpr int kStages = 4;
+constexpr int kWSlots = 2;
+constexpr int kDoneSlots = 8;       // > kStages: the producer is never further ahead than that
+constexpr int kRegsProducer = 40, kRegsAlpha = 104, kRegsFeature = 184;
 
 template <int CH>
 struct alignas(128) Stage {
@@ -29,67 +49,101 @@ struct alignas(128) Stage {
     uint32_t listpos[kStageEntries];              // 1-based position in the tile's list (reference `contributor`)
     uint32_t gid[kStageEntries];                  // Gaussian index
     uint32_t n;                                   // valid entries
-    uint32_t last;                                // 1 = no further stage follows
+    uint32_t last;                                // 1 = last stage of this work item
+    uint32_t first;                               // 1 = first stage of this work item
+    int32_t work;                                 // work item (tile * chunks + chunk); < 0: no more work
 };
 
-template <int CH, int STAGES>
-struct alignas(128) Ring {
-    Stage<CH> stage[STAGES];
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
-    uint32_t done_mask;  // bit w set: consumer warp w needs no more instances
+struct alignas(128) WSlot {
+    float w[kStageEntries][32];    // blend weights [instance][pixel of the block]
+    uint32_t pm[kStageEntries];    // per instance: which pixels blended
+    uint32_t km;                   // which instances have pm != 0
+    uint32_t last;
+    uint32_t first;
+    int32_t work;
 };
 
-// pixel <-> lane mapping inside a warp's 8x4 block: 2x2 quads, quad q = lane>>2 laid out 4 across
+template <int CH>
+struct alignas(128) RingV2 {
+    Stage<CH> stage[kStages];
+    WSlot ws[kBlocksPerTile][kWSlots];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t wfull[kBlocksPerTile][kWSlots];
+    uint64_t wempty[kBlocksPerTile][kWSlots];
+    uint32_t done_mask[kDoneSlots];  // bit b set: pixel block b of that work item needs no more instances
+};
+
+// pixel <-> lane mapping inside a block: 2x2 quads, quad q = lane>>2 laid out 4 across
 __device__ __forceinline__ int lane_px(int lane) { return ((lane >> 2) & 3) * 2 + (lane & 1); }
 __device__ __forceinline__ int lane_py(int lane) { return (lane >> 4) * 2 + ((lane >> 1) & 1); }
 
-template <int CH, int STAGES>
-__device__ __forceinline__ void ring_init(Ring<CH, STAGES>& ring) {
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+template <int CH>
+__device__ __forceinline__ void ring_init(RingV2<CH>& ring, int n_stage_consumers, bool use_w) {
     // called by all threads before the role split; followed by __syncthreads()
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) {
+        for (int s = 0; s < kStages; s++) {
             mbar_init(&ring.full[s], 1);
-            mbar_init(&ring.empty[s], kConsumerWarps);
+            mbar_init(&ring.empty[s], n_stage_consumers);
         }
-        ring.done_mask = 0;
+        for (int b = 0; b < kBlocksPerTile; b++)
+            for (int j = 0; j < kWSlots; j++) {
+                mbar_init(&ring.wfull[b][j], 1);
+                mbar_init(&ring.wempty[b][j], 1);
+            }
+        for (int i = 0; i < kDoneSlots; i++) ring.done_mask[i] = 0;
         mbar_fence_init();
     }
+    (void)use_w;
     if (CH > 0) {
         // rows shorter than CH (last channel chunk) rely on zero padding
         float4* p = reinterpret_cast<float4*>(&ring.stage[0]);
-        const int n16 = (int)(sizeof(Stage<CH>) * STAGES / 16);
+        const int n16 = (int)(sizeof(Stage<CH>) * kStages / 16);
         for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         // order these generic-proxy stores before the async-proxy (bulk copy) writes to the same rows
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
 }
 
-// Producer warp.  REVERSE: walk the list back to front starting at `first` (backward pass).
-// row_floats > 0: copy `row_floats` floats of features + gid*C + chunk_off per entry.
-template <int CH, int STAGES, bool REVERSE>
-__device__ __forceinline__ void producer_loop(Ring<CH, STAGES>& ring, const uint32_t* __restrict__ point_list,
-                                              const SplatRec* __restrict__ rec, const float* __restrict__ features,
-                                              int C, int chunk_off, int row_floats, bool use_bulk,
-                                              uint32_t range_begin, uint32_t range_end, uint32_t walk_count,
-                                              float tx0, float ty0, float tx1, float ty1) {
+// Everything the producer needs to know about the view.
+struct ProducerArgs {
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const SplatRec* rec;
+    const float* features;      // nullptr: no feature rows (backward, or C == 0)
+    const uint32_t* n_contrib;  // backward only: bounds the reverse walk
+    int* work_counter;
+    int W, H, C;
+    int tiles_x, num_tiles, chunks;
+    int use_bulk;
+};
+
+// Producer warp: persistent over work items.  REVERSE: walk each list back to front (backward pass).
+template <int CH, bool REVERSE>
+__device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerArgs& pa) {
     const int lane = threadIdx.x & 31;
     int s = 0;
     uint32_t empty_parity = 1;  // fresh barrier: waiting on parity 1 falls through
-    uint32_t fill = 0;
-    const uint32_t row_bytes = (uint32_t)row_floats * 4u;
-
     mbar_wait(&ring.empty[0], empty_parity);
 
-    auto list_index = [&](uint32_t i) -> uint32_t {  // i-th visited element -> index into point_list
-        return REVERSE ? (range_begin + walk_count - 1 - i) : (range_begin + i);
-    };
-    auto publish = [&](uint32_t n, uint32_t last) {
+    auto publish = [&](uint32_t n, uint32_t last, uint32_t first, int work, uint32_t row_bytes) {
         __syncwarp();
         if (lane == 0) {
-            ring.stage[s].n = n;
-            ring.stage[s].last = last;
-            if (CH > 0 && use_bulk && n > 0)
+            Stage<CH>& st = ring.stage[s];
+            st.n = n;
+            st.last = last;
+            st.first = first;
+            st.work = work;
+            if (CH > 0 && pa.features != nullptr && pa.use_bulk && n > 0)
                 mbar_arrive_expect_tx(&ring.full[s], n * row_bytes);
             else
                 mbar_arrive(&ring.full[s]);
@@ -98,80 +152,119 @@ __device__ __forceinline__ void producer_loop(Ring<CH, STAGES>& ring, const uint
     };
     auto advance = [&]() {
         s++;
-        if (s == STAGES) {
+        if (s == kStages) {
             s = 0;
             empty_parity ^= 1;
         }
         mbar_wait(&ring.empty[s], empty_parity);
     };
-    auto store_entry = [&](uint32_t slot, uint32_t gid, uint32_t lpos, float4 r0, float4 r1, float4 r2) {
-        Stage<CH>& st = ring.stage[s];
-        st.rec0[slot] = r0;
-        st.rec1[slot] = r1;
-        st.rec2[slot] = r2;
-        st.listpos[slot] = lpos;
-        st.gid[slot] = gid;
-        if (CH > 0) {
-            const float* src = features + (size_t)gid * C + chunk_off;
-            if (use_bulk) {
-                bulk_g2s(&st.feat[slot][0], src, row_bytes, &ring.full[s]);
-            } else {
-                for (int c = 0; c < row_floats; c++) st.feat[slot][c] = __ldg(src + c);
+
+    const int num_work = pa.num_tiles * pa.chunks;
+    for (;;) {
+        int work = 0;
+        if (lane == 0) work = atomicAdd(pa.work_counter, 1);
+        work = __shfl_sync(0xffffffffu, work, 0);
+        if (work >= num_work) {
+            publish(0, 1, 1, -1, 0);
+            break;
+        }
+        const int tile = work / pa.chunks, chunk = work - tile * pa.chunks;
+        const int tile_x = tile % pa.tiles_x, tile_y = tile / pa.tiles_x;
+        const uint2 range = pa.ranges[tile];
+        const uint32_t range_begin = range.x;
+        uint32_t walk_count = range.y - range.x;
+        if (REVERSE) {
+            // nothing behind the deepest last-contributor of the tile is ever used
+            uint32_t tmax = 0;
+            const int yy = tile_y * 16 + (lane >> 1), xb = tile_x * 16 + (lane & 1) * 8;
+            if (yy < pa.H)
+                for (int i = 0; i < 8; i++)
+                    if (xb + i < pa.W) tmax = max(tmax, pa.n_contrib[(size_t)yy * pa.W + xb + i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            walk_count = min(walk_count, tmax);
+        }
+        const float tx0 = (float)(tile_x * 16), ty0 = (float)(tile_y * 16), tx1 = tx0 + 15.f, ty1 = ty0 + 15.f;
+        const int chunk_off = chunk * CH;
+        const int row_floats = (CH > 0 && pa.features != nullptr) ? min(CH, pa.C - chunk_off) : 0;
+        const uint32_t row_bytes = (uint32_t)row_floats * 4u;
+        uint32_t* done = &ring.done_mask[work % kDoneSlots];
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(done) = 0;
+        __syncwarp();
+
+        auto list_index = [&](uint32_t i) -> uint32_t {  // i-th visited element -> index into point_list
+            return REVERSE ? (range_begin + walk_count - 1 - i) : (range_begin + i);
+        };
+        auto store_entry = [&](uint32_t slot, uint32_t gid, uint32_t lpos, float4 r0, float4 r1, float4 r2) {
+            Stage<CH>& st = ring.stage[s];
+            st.rec0[slot] = r0;
+            st.rec1[slot] = r1;
+            st.rec2[slot] = r2;
+            st.listpos[slot] = lpos;
+            st.gid[slot] = gid;
+            if (CH > 0 && row_floats > 0) {
+                const float* src = pa.features + (size_t)gid * pa.C + chunk_off;
+                if (pa.use_bulk) {
+                    bulk_g2s(&st.feat[slot][0], src, row_bytes, &ring.full[s]);
+                } else {
+                    for (int c = 0; c < row_floats; c++) st.feat[slot][c] = __ldg(src + c);
+                }
+            }
+        };
+
+        uint32_t fill = 0, first = 1;
+        // two-deep software pipeline on the dependent loads (list index -> id -> record)
+        const uint32_t nchunks = (walk_count + 31) / 32;
+        uint32_t id_cur = 0, id_nxt = 0;
+        float4 a0, a1, a2;
+        a0 = a1 = a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nchunks > 0) {
+            if (lane < walk_count) id_cur = pa.point_list[list_index(lane)];
+            if (32 + lane < walk_count) id_nxt = pa.point_list[list_index(32 + lane)];
+            if (lane < walk_count) {
+                const float4* r = reinterpret_cast<const float4*>(pa.rec + id_cur);
+                a0 = __ldg(r); a1 = __ldg(r + 1); a2 = __ldg(r + 2);
             }
         }
-    };
+        for (uint32_t c = 0; c < nchunks; c++) {
+            if (*reinterpret_cast<volatile uint32_t*>(done) == (1u << kBlocksPerTile) - 1u) break;
+            float4 b0, b1, b2;
+            b0 = b1 = b2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t i1 = (c + 1) * 32 + lane, i2 = (c + 2) * 32 + lane;
+            uint32_t id_nn = 0;
+            if (i1 < walk_count) {
+                const float4* r = reinterpret_cast<const float4*>(pa.rec + id_nxt);
+                b0 = __ldg(r); b1 = __ldg(r + 1); b2 = __ldg(r + 2);
+            }
+            if (i2 < walk_count) id_nn = pa.point_list[list_index(i2)];
 
-    // two-deep software pipeline on the dependent loads (list index -> id -> record)
-    const uint32_t nchunks = (walk_count + 31) / 32;
-    uint32_t id_nxt = 0;     // ids of chunk c+1
-    float4 a0, a1, a2;       // records of chunk c
-    uint32_t id_cur = 0;
-    a0 = a1 = a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (nchunks > 0) {
-        if (lane < walk_count) id_cur = point_list[list_index(lane)];
-        if (32 + lane < walk_count) id_nxt = point_list[list_index(32 + lane)];
-        if (lane < walk_count) {
-            const float4* r = reinterpret_cast<const float4*>(rec + id_cur);
-            a0 = __ldg(r); a1 = __ldg(r + 1); a2 = __ldg(r + 2);
+            const uint32_t i0 = c * 32 + lane;
+            const bool valid = i0 < walk_count;
+            // does the alpha >= 1/255 footprint reach this tile?  (conservative, see alpha_extent)
+            const bool keep = valid && (a0.x + a0.z >= tx0) && (a0.x - a0.z <= tx1) && (a0.y + a0.w >= ty0) &&
+                              (a0.y - a0.w <= ty1);
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            const uint32_t cnt = __popc(m);
+            const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            const uint32_t lpos = list_index(i0) - range_begin + 1;
+            const uint32_t room = kStageEntries - fill;
+            if (keep && rank < room) store_entry(fill + rank, id_cur, lpos, a0, a1, a2);
+            if (cnt >= room) {
+                publish(kStageEntries, 0, first, work, row_bytes);
+                first = 0;
+                advance();
+                if (keep && rank >= room) store_entry(rank - room, id_cur, lpos, a0, a1, a2);
+                fill = cnt - room;
+            } else {
+                fill += cnt;
+            }
+            a0 = b0; a1 = b1; a2 = b2;
+            id_cur = id_nxt;
+            id_nxt = id_nn;
         }
+        publish(fill, 1, first, work, row_bytes);
+        advance();
     }
-    for (uint32_t c = 0; c < nchunks; c++) {
-        if (*reinterpret_cast<volatile uint32_t*>(&ring.done_mask) == (1u << kConsumerWarps) - 1u) break;
-        // prefetch: records of chunk c+1, ids of chunk c+2
-        float4 b0, b1, b2;
-        b0 = b1 = b2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t i1 = (c + 1) * 32 + lane, i2 = (c + 2) * 32 + lane;
-        uint32_t id_nn = 0;
-        if (i1 < walk_count) {
-            const float4* r = reinterpret_cast<const float4*>(rec + id_nxt);
-            b0 = __ldg(r); b1 = __ldg(r + 1); b2 = __ldg(r + 2);
-        }
-        if (i2 < walk_count) id_nn = point_list[list_index(i2)];
-
-        const uint32_t i0 = c * 32 + lane;
-        const bool valid = i0 < walk_count;
-        // does the alpha >= 1/255 footprint reach this tile?  (conservative, see alpha_extent)
-        const bool keep = valid && (a0.x + a0.z >= tx0) && (a0.x - a0.z <= tx1) && (a0.y + a0.w >= ty0) &&
-                          (a0.y - a0.w <= ty1);
-        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        const uint32_t cnt = __popc(m);
-        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-        const uint32_t lpos = list_index(i0) - range_begin + 1;
-        const uint32_t room = kStageEntries - fill;
-        if (keep && rank < room) store_entry(fill + rank, id_cur, lpos, a0, a1, a2);
-        if (cnt >= room) {
-            publish(kStageEntries, 0);
-            advance();
-            if (keep && rank >= room) store_entry(rank - room, id_cur, lpos, a0, a1, a2);
-            fill = cnt - room;
-        } else {
-            fill += cnt;
-        }
-        a0 = b0; a1 = b1; a2 = b2;
-        id_cur = id_nxt;
-        id_nxt = id_nn;
-    }
-    publish(fill, 1);
 }
 
 }  // namespace f3dgs

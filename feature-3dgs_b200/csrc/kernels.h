@@ -46,7 +46,7 @@ void launch_tile_ranges(int R, const uint64_t* sorted_keys, uint2* ranges, cudaS
 cudaError_t launch_composite_fwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                  const SplatRec* rec, const float* features, const float* bg,
                                  float* final_T, uint32_t* n_contrib, float* out_color,
-                                 float* out_feature, float* out_depth, cudaStream_t s);
+                                 float* out_feature, float* out_depth, int* work_counter, cudaStream_t s);
 
 // ---- composite_bwd.cu
 cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
@@ -54,6 +54,6 @@ cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, cons
                                  const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dfeat_pix,
                                  const float* dL_ddepth, float* dL_dmean2D, float* dL_dconic,
                                  float* dL_dopacity, float* dL_dcolor, float* dL_dfeature, float* dL_dz,
-                                 cudaStream_t s);
+                                 int* work_counter, cudaStream_t s);
 
 }  // namespace f3dgs

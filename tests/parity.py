@@ -164,23 +164,38 @@ def float_mismatch(a, b, rtol=RTOL, atol_rel=ATOL_REL):
 
 
 def compare(ours, ref, int_keys=INT_KEYS, float_keys=FWD_FLOAT_KEYS, grad_keys=GRAD_KEYS, rtol=RTOL,
-            atol_rel=ATOL_REL):
-    """-> dict report; report['ok'] is the overall verdict."""
+            atol_rel=ATOL_REL, tie_tolerant=False):
+    """-> dict report; report['ok'] is the overall verdict.
+
+    tie_tolerant (CPU-oracle comparisons only): libm's expf differs from CUDA's by <= 2 ulp, so a pixel whose
+    alpha or T lands within an ulp of the 1/255 or 1e-4 threshold can blend one Gaussian more or less.  Up to
+    max(2, 1e-4 * pixels) such n_contrib mismatches are accepted; those pixels are masked out of the image
+    comparison and, if any occurred, the gradient tolerance is widened 50x (a single flipped blend shows up in a
+    few Gaussians' gradients).  The comparison against the reference CUDA build never uses this."""
     rep, ok = {}, True
+    tie_mask, ties = None, 0
     for k in int_keys:
         a, b = np.asarray(ours[k]), np.asarray(ref[k])
         same = a.shape == b.shape and bool(np.array_equal(a, b))
         n_bad = int(np.sum(a != b)) if a.shape == b.shape else -1
         rep[k] = dict(exact=same, mismatches=n_bad, size=int(b.size))
+        if k == "n_contrib" and tie_tolerant and not same and 0 < n_bad <= max(2, int(1e-4 * b.size)):
+            tie_mask, ties = (a != b), n_bad
+            rep[k]["accepted_ties"] = n_bad
+            continue
         ok &= same
     for k in float_keys:
-        r, e, s = float_mismatch(ours[k], ref[k], rtol, atol_rel)
+        a, b = np.asarray(ours[k]), np.asarray(ref[k])
+        if tie_mask is not None and a.shape == b.shape and a.shape[-2:] == tie_mask.shape:
+            a = np.where(tie_mask, b, a)
+        r, e, s = float_mismatch(a, b, rtol, atol_rel)
         rep[k] = dict(ratio=r, max_abs_err=e, scale=s, bit_exact=bool(np.array_equal(ours[k], ref[k])))
         ok &= r <= 1.0
     if "grads" in ours and "grads" in ref:
+        widen = 50.0 if ties else 1.0
         for k in grad_keys:
             if k in ours["grads"] and k in ref["grads"]:
-                r, e, s = float_mismatch(ours["grads"][k], ref["grads"][k], rtol, atol_rel)
+                r, e, s = float_mismatch(ours["grads"][k], ref["grads"][k], rtol * widen, atol_rel * widen)
                 rep["grad_" + k] = dict(ratio=r, max_abs_err=e, scale=s)
                 ok &= r <= 1.0
     rep["ok"] = bool(ok)
@@ -193,7 +208,8 @@ def format_report(rep):
         if k == "ok":
             continue
         if "exact" in v:
-            lines.append(f"  {k:22s} exact={v['exact']} mismatches={v['mismatches']}/{v['size']}")
+            t = f" (accepted threshold ties: {v['accepted_ties']})" if "accepted_ties" in v else ""
+            lines.append(f"  {k:22s} exact={v['exact']} mismatches={v['mismatches']}/{v['size']}{t}")
         else:
             extra = f" bit_exact={v['bit_exact']}" if "bit_exact" in v else ""
             lines.append(f"  {k:22s} viol={v['ratio']:.3g} max_abs_err={v['max_abs_err']:.3g} scale={v['scale']:.3g}{extra}")

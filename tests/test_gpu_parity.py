@@ -44,7 +44,7 @@ def _check(sc, cam, with_grads=True, vs_ref=True, vs_oracle=True, exact_vs_ref=T
         orc = parity.run_oracle(sc, cam, grads=grads, threads=1, **okw)
         gk = tuple(k for k in ("means3D", "means2D", "sh", "semantic_feature", "opacities", "scales", "rotations",
                                "colors_precomp", "cov3D_precomp") if grads is not None and k in ours["grads"])
-        rep = parity.compare(ours, orc, grad_keys=gk)
+        rep = parity.compare(ours, orc, grad_keys=gk, tie_tolerant=True)
         assert rep["ok"], "vs CPU oracle:\n" + parity.format_report(rep)
         n += 1
     assert n > 0
