@@ -27,8 +27,8 @@ constexpr int kRedRows = kRedSlots * kRedVals;
 
 struct alignas(128) BwdSmem {
     RingV2<0> ring;
-    float red[kAlphaWarps][kRedRows][33];
-    uint32_t red_gid[kAlphaWarps][kRedSlots];
+    float red[kBlocksPerTile][kRedRows][33];
+    uint32_t red_gid[kBlocksPerTile][kRedSlots];
 };
 
 struct BwdArgs {
@@ -48,8 +48,8 @@ struct BwdArgs {
     int vec_io;          // bit0: 128-bit loads of dL_dfeat_pix, bit1: red.v4 into dL_dfeature
 };
 
-template <int CH>
-__global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdArgs args) {
+template <int CH, int BPA>
+__global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel(const BwdArgs args) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     RingV2<0>& ring = sm.ring;
@@ -57,20 +57,21 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
     const size_t HW = (size_t)H * W;
 
-    ring_init(ring, CH > 0 ? kAlphaWarps + kBlocksPerTile : kAlphaWarps, CH > 0);
+    using L = Layout<BPA>;
+    ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
     __syncthreads();
 
     // ======================================================================== producer group
     if (warp < kAlphaWarp0) {
-        reg_dec<kRegsProducer>();
+        reg_dec<L::kRegsProducer>();
         if (warp == kProducerWarp) producer_loop<0, true>(ring, args.pa);
         return;
     }
 
     // ======================================================================== alpha warps
-    if (warp < kFeatWarp0) {
-        reg_dec<kRegsAlpha>();
-        const int a = warp - kAlphaWarp0;  // owns blocks 2a and 2a+1
+    if (warp < L::kFeatWarp0) {
+        reg_dec<L::kRegsAlpha>();
+        const int a = warp - kAlphaWarp0;  // owns blocks BPA*a .. BPA*a + BPA-1
         float(*red)[33] = sm.red[a];
         uint32_t* red_gid = sm.red_gid[a];
         uint32_t nslots = 0;  // warp-uniform; rows of both blocks share the scratch
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
             float ar0, ar1, ar2, lc0, lc1, lc2, last_alpha, accum_depth, last_depth;
             uint32_t last_contrib, wmax;
             bool inside;
-        } P[2];
+        } P[BPA];
 #pragma unroll
-        for (int bi = 0; bi < 2; bi++) {
+        for (int bi = 0; bi < BPA; bi++) {
             P[bi] = Px{};
         }
         bool do_geom = false;
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
                 const int tile_x = tile % args.pa.tiles_x, tile_y = tile / args.pa.tiles_x;
                 do_geom = (chunk == 0);
 #pragma unroll
-                for (int bi = 0; bi < 2; bi++) {
-                    const int b = 2 * a + bi;
+                for (int bi = 0; bi < BPA; bi++) {
+                    const int b = BPA * a + bi;
                     Px& p = P[bi];
                     const int bx0 = tile_x * 16 + (b & 1) * 8, by0 = tile_y * 16 + (b >> 1) * 4;
                     const int px = bx0 + lane_px(lane), py = by0 + lane_py(lane);
@@ -161,8 +162,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
                 }
             }
 #pragma unroll
-            for (int bi = 0; bi < 2; bi++) {
-                const int b = 2 * a + bi;
+            for (int bi = 0; bi < BPA; bi++) {
+                const int b = BPA * a + bi;
                 Px& p = P[bi];
                 WSlot* ws = &ring.ws[b][j];
                 if (CH > 0) mbar_wait(&ring.wempty[b][j], wparity);
@@ -276,8 +277,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
         }
         if (CH > 0) {
 #pragma unroll
-            for (int bi = 0; bi < 2; bi++) {
-                const int b = 2 * a + bi;
+            for (int bi = 0; bi < BPA; bi++) {
+                const int b = BPA * a + bi;
                 mbar_wait(&ring.wempty[b][j], wparity);
                 if (lane == 0) {
                     ring.ws[b][j].work = -1;
@@ -291,12 +292,12 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
 
     // ======================================================================== feature warps
     if (CH == 0) return;
-    reg_inc<kRegsFeature>();
+    reg_inc<L::kRegsFeature>();
     {
         constexpr int LPR = CH > 0 ? CH / 4 : 32;
         constexpr int G = 32 / LPR;
         constexpr int NQ = 8 / G;
-        const int b = warp - kFeatWarp0;
+        const int b = warp - L::kFeatWarp0;
         const int grp = lane / LPR, cl = lane % LPR;
         float dO[NQ][4][4];  // upstream feature gradient: [quad][pixel in quad][channel]
         int s = 0, j = 0, ch0 = 0;
@@ -361,13 +362,17 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
                 const uint32_t pm = ws.pm[k];
                 const uint32_t gid = st.gid[k];
                 float4 w4[NQ];
+                if (L::kPrefetchW) {
 #pragma unroll
-                for (int qi = 0; qi < NQ; qi++) w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
+                    for (int qi = 0; qi < NQ; qi++)
+                        w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
+                }
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
                 for (int qi = 0; qi < NQ; qi++) {
                     const int q = qi * G + grp;
                     if ((pm >> (4 * q)) & 0xFu) {
+                        if (!L::kPrefetchW) w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * q]);
                         const float wv[4] = {w4[qi].x, w4[qi].y, w4[qi].z, w4[qi].w};
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
@@ -408,13 +413,15 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_bwd_kernel(const BwdA
     }
 }
 
-template <int CH>
+int composite_layout_bpa(int default_bpa);  // composite_fwd.cu
+
+template <int CH, int BPA>
 static cudaError_t launch_bwd_t(const ViewParams& vp, BwdArgs a, cudaStream_t s) {
     const size_t smem = sizeof(BwdSmem);
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<CH, BPA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -429,10 +436,13 @@ static cudaError_t launch_bwd_t(const ViewParams& vp, BwdArgs a, cudaStream_t s)
     cudaError_t e = cudaMemsetAsync(a.pa.work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms > 0 ? num_sms : 148);
-    composite_bwd_kernel<CH><<<grid, kThreadsV2, smem, s>>>(a);
+    composite_bwd_kernel<CH, BPA><<<grid, Layout<BPA>::kThreads, smem, s>>>(a);
     g_launches++;
     return cudaGetLastError();
 }
+
+#define F3DGS_BWD_DISPATCH(CHV) \
+    (composite_layout_bpa(1) == 2 ? launch_bwd_t<CHV, 2>(vp, a, s) : launch_bwd_t<CHV, 1>(vp, a, s))
 
 cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                  const SplatRec* rec, const float* bg, const float* final_T,
@@ -449,10 +459,10 @@ cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, cons
     a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib; a.dL_dpix = dL_dpix; a.dL_dfeat_pix = dL_dfeat_pix;
     a.dL_ddepth = dL_ddepth; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
     a.dL_dcolor = dL_dcolor; a.dL_dfeature = dL_dfeature; a.dL_dz = dL_dz; a.vec_io = 0;
-    if (vp.C == 0) return launch_bwd_t<0>(vp, a, s);
-    if (vp.C <= 32) return launch_bwd_t<32>(vp, a, s);
-    if (vp.C <= 64) return launch_bwd_t<64>(vp, a, s);
-    return launch_bwd_t<128>(vp, a, s);
+    if (vp.C == 0) return F3DGS_BWD_DISPATCH(0);
+    if (vp.C <= 32) return F3DGS_BWD_DISPATCH(32);
+    if (vp.C <= 64) return F3DGS_BWD_DISPATCH(64);
+    return F3DGS_BWD_DISPATCH(128);
 }
 
 }  // namespace f3dgs

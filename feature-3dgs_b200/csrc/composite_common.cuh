@@ -30,15 +30,27 @@ namespace f3dgs {
 
 constexpr int kBlocksPerTile = 8;   // 8x4-pixel blocks in a 16x16 tile
 constexpr int kProducerWarp = 0;    // warps 0..3: producer warpgroup (warps 1..3 retire at once)
-constexpr int kAlphaWarp0 = 4;      // warps 4..7, two pixel blocks each
-constexpr int kAlphaWarps = 4;
-constexpr int kFeatWarp0 = 8;       // warps 8..15, one pixel block each
-constexpr int kThreadsV2 = 16 * 32;
+constexpr int kAlphaWarp0 = 4;      // alpha warps follow, BPA pixel blocks each; then 8 feature warps
+
+// Warp/register layout, selected by BPA = pixel blocks per alpha warp:
+//   BPA = 2: 4 alpha + 8 feature + producer group = 16 warps, launched with 128 regs (all 64K);
+//            setmaxnreg: producer 40 / alpha 104 / feature 184
+//   BPA = 1: 8 alpha + 8 feature + producer group = 20 warps, launched with 96 regs (61440);
+//            setmaxnreg: producer 40 / alpha 64 / feature 152
+template <int BPA>
+struct Layout {
+    static constexpr int kAlphaWarps = kBlocksPerTile / BPA;
+    static constexpr int kFeatWarp0 = kAlphaWarp0 + kAlphaWarps;
+    static constexpr int kThreads = (kFeatWarp0 + kBlocksPerTile) * 32;
+    static constexpr int kRegsProducer = 40;
+    static constexpr int kRegsAlpha = BPA == 2 ? 104 : 64;
+    static constexpr int kRegsFeature = BPA == 2 ? 184 : 152;
+    static constexpr bool kPrefetchW = BPA == 2;  // room to hold all weight quads + the next instance's row
+};
 constexpr int kStageEntries = 32;
 constexpr int kStages = 4;
 constexpr int kWSlots = 2;
 constexpr int kDoneSlots = 8;       // > kStages: the producer is never further ahead than that
-constexpr int kRegsProducer = 40, kRegsAlpha = 104, kRegsFeature = 184;
 
 template <int CH>
 struct alignas(128) Stage {
@@ -121,7 +133,7 @@ struct ProducerArgs {
     const SplatRec* rec;
     const float* features;      // nullptr: no feature rows (backward, or C == 0)
     const uint32_t* n_contrib;  // backward only: bounds the reverse walk
-    int* work_counter;
+    int* work_counter;          // zeroed by the launcher; tiles are handed out with atomicAdd
     int W, H, C;
     int tiles_x, num_tiles, chunks;
     int use_bulk;

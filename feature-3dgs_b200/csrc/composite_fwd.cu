@@ -17,6 +17,8 @@
 //                  channels (= 128 accumulators per lane at CH = 128) live in registers.
 // Channel counts above 128 are split into chunks of 128 (extra work items); chunk 0 also writes
 // colour, depth, final_T and n_contrib.
+#include <cstdlib>
+
 #include "composite_common.cuh"
 
 namespace f3dgs {
@@ -32,36 +34,37 @@ struct FwdArgs {
     int vec_store;
 };
 
-template <int CH>
-__global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdArgs args) {
+template <int CH, int BPA>
+__global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel(const FwdArgs args) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RingV2<CH>& ring = *reinterpret_cast<RingV2<CH>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
     const size_t HW = (size_t)H * W;
 
-    ring_init(ring, CH > 0 ? kAlphaWarps + kBlocksPerTile : kAlphaWarps, CH > 0);
+    using L = Layout<BPA>;
+    ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
     __syncthreads();
 
     // ======================================================================== producer group
     if (warp < kAlphaWarp0) {
-        reg_dec<kRegsProducer>();
+        reg_dec<L::kRegsProducer>();
         if (warp == kProducerWarp) producer_loop<CH, false>(ring, args.pa);
         return;
     }
 
     // ======================================================================== alpha warps
-    if (warp < kFeatWarp0) {
-        reg_dec<kRegsAlpha>();
-        const int a = warp - kAlphaWarp0;  // owns blocks 2a and 2a+1
+    if (warp < L::kFeatWarp0) {
+        reg_dec<L::kRegsAlpha>();
+        const int a = warp - kAlphaWarp0;  // owns blocks BPA*a .. BPA*a + BPA-1
         int s = 0, j = 0;
         uint32_t parity = 0, wparity = 1;  // wempty: fresh barrier falls through on parity 1
-        float T[2], Cr[2], Cg[2], Cb[2], Dp[2], pxf[2], pyf[2], fbx0[2], fby0[2];
-        uint32_t last_contrib[2];
-        int px[2], py[2], chunk = 0;
-        bool done[2], inside[2], blk_done[2];
+        float T[BPA], Cr[BPA], Cg[BPA], Cb[BPA], Dp[BPA], pxf[BPA], pyf[BPA], fbx0[BPA], fby0[BPA];
+        uint32_t last_contrib[BPA];
+        int px[BPA], py[BPA], chunk = 0;
+        bool done[BPA], inside[BPA], blk_done[BPA];
 #pragma unroll
-        for (int bi = 0; bi < 2; bi++) {
+        for (int bi = 0; bi < BPA; bi++) {
             T[bi] = 1.f; Cr[bi] = Cg[bi] = Cb[bi] = Dp[bi] = 0.f; pxf[bi] = pyf[bi] = fbx0[bi] = fby0[bi] = 0.f;
             last_contrib[bi] = 0; px[bi] = py[bi] = 0; done[bi] = true; inside[bi] = false; blk_done[bi] = true;
         }
@@ -76,8 +79,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
                 chunk = work - tile * args.pa.chunks;
                 const int tile_x = tile % args.pa.tiles_x, tile_y = tile / args.pa.tiles_x;
 #pragma unroll
-                for (int bi = 0; bi < 2; bi++) {
-                    const int b = 2 * a + bi;
+                for (int bi = 0; bi < BPA; bi++) {
+                    const int b = BPA * a + bi;
                     const int bx0 = tile_x * 16 + (b & 1) * 8, by0 = tile_y * 16 + (b >> 1) * 4;
                     px[bi] = bx0 + lane_px(lane);
                     py[bi] = by0 + lane_py(lane);
@@ -92,8 +95,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
                 }
             }
 #pragma unroll
-            for (int bi = 0; bi < 2; bi++) {
-                const int b = 2 * a + bi;
+            for (int bi = 0; bi < BPA; bi++) {
+                const int b = BPA * a + bi;
                 WSlot* ws = &ring.ws[b][j];
                 if (CH > 0) mbar_wait(&ring.wempty[b][j], wparity);
                 uint32_t km = 0;
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
             if (lane == 0) mbar_arrive(&ring.empty[s]);
             if (last && chunk == 0) {
 #pragma unroll
-                for (int bi = 0; bi < 2; bi++)
+                for (int bi = 0; bi < BPA; bi++)
                     if (inside[bi]) {
                         const size_t pix = (size_t)py[bi] * W + px[bi];
                         args.final_T[pix] = T[bi];
@@ -194,8 +197,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
         }
         if (CH > 0) {  // tell the feature warps of these blocks that the work is over
 #pragma unroll
-            for (int bi = 0; bi < 2; bi++) {
-                const int b = 2 * a + bi;
+            for (int bi = 0; bi < BPA; bi++) {
+                const int b = BPA * a + bi;
                 mbar_wait(&ring.wempty[b][j], wparity);
                 if (lane == 0) {
                     ring.ws[b][j].work = -1;
@@ -209,12 +212,12 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
 
     // ======================================================================== feature warps
     if (CH == 0) return;
-    reg_inc<kRegsFeature>();
+    reg_inc<L::kRegsFeature>();
     {
         constexpr int LPR = CH > 0 ? CH / 4 : 32;  // lanes per feature row
         constexpr int G = 32 / LPR;                // lane groups sharing the 32 pixels
         constexpr int NQ = 8 / G;                  // 2x2 quads per lane
-        const int b = warp - kFeatWarp0;
+        const int b = warp - L::kFeatWarp0;
         const int grp = lane / LPR, cl = lane % LPR;
         float acc[NQ][4][4];  // [quad][pixel in quad][channel]
 #pragma unroll
@@ -234,30 +237,56 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
             const uint32_t last = ws.last;
             mbar_wait(&ring.full[s], parity);  // feature rows of this stage have landed
             const Stage<CH>& st = ring.stage[s];
-            if (km) {
-                // software pipeline over the blended instances: the next instance's mask and feature
-                // float4 are fetched while the current one is being accumulated; all weight quads of
-                // the current instance are loaded up front so no LDS sits between the FFMA blocks
-                int k = __ffs(km) - 1;
-                km &= km - 1;
-                uint32_t pm = ws.pm[k];
-                float4 f = *reinterpret_cast<const float4*>(&st.feat[k][cl * 4]);
-                for (;;) {
-                    float4 w4[NQ];
-#pragma unroll
-                    for (int qi = 0; qi < NQ; qi++)
-                        w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
-                    const bool more = km != 0;
-                    const int kn = more ? (__ffs(km) - 1) : k;
+            if (L::kPrefetchW) {
+                if (km) {
+                    // software pipeline over the blended instances: the next instance's mask and feature
+                    // float4 are fetched while the current one is being accumulated; all weight quads of
+                    // the current instance are loaded up front so no LDS sits between the FFMA blocks
+                    int k = __ffs(km) - 1;
                     km &= km - 1;
-                    const uint32_t pmn = ws.pm[kn];
-                    const float4 fn = *reinterpret_cast<const float4*>(&st.feat[kn][cl * 4]);
+                    uint32_t pm = ws.pm[k];
+                    float4 f = *reinterpret_cast<const float4*>(&st.feat[k][cl * 4]);
+                    for (;;) {
+                        float4 w4[NQ];
+#pragma unroll
+                        for (int qi = 0; qi < NQ; qi++)
+                            w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
+                        const bool more = km != 0;
+                        const int kn = more ? (__ffs(km) - 1) : k;
+                        km &= km - 1;
+                        const uint32_t pmn = ws.pm[kn];
+                        const float4 fn = *reinterpret_cast<const float4*>(&st.feat[kn][cl * 4]);
+#pragma unroll
+                        for (int qi = 0; qi < NQ; qi++) {
+                            const int q = qi * G + grp;
+                            if ((pm >> (4 * q)) & 0xFu) {
+                                // a pixel that skipped this instance stored w = 0: adds exactly 0
+                                const float wv[4] = {w4[qi].x, w4[qi].y, w4[qi].z, w4[qi].w};
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    acc[qi][i][0] = fmaf(f.x, wv[i], acc[qi][i][0]);
+                                    acc[qi][i][1] = fmaf(f.y, wv[i], acc[qi][i][1]);
+                                    acc[qi][i][2] = fmaf(f.z, wv[i], acc[qi][i][2]);
+                                    acc[qi][i][3] = fmaf(f.w, wv[i], acc[qi][i][3]);
+                                }
+                            }
+                        }
+                        if (!more) break;
+                        k = kn; pm = pmn; f = fn;
+                    }
+                }
+            } else {
+                while (km) {
+                    const int k = __ffs(km) - 1;
+                    km &= km - 1;
+                    const uint32_t pm = ws.pm[k];
+                    const float4 f = *reinterpret_cast<const float4*>(&st.feat[k][cl * 4]);
 #pragma unroll
                     for (int qi = 0; qi < NQ; qi++) {
                         const int q = qi * G + grp;
                         if ((pm >> (4 * q)) & 0xFu) {
-                            // a pixel that skipped this instance stored w = 0: adds exactly 0
-                            const float wv[4] = {w4[qi].x, w4[qi].y, w4[qi].z, w4[qi].w};
+                            const float4 w4 = *reinterpret_cast<const float4*>(&ws.w[k][4 * q]);
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
                                 acc[qi][i][0] = fmaf(f.x, wv[i], acc[qi][i][0]);
@@ -267,8 +296,6 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
                             }
                         }
                     }
-                    if (!more) break;
-                    k = kn; pm = pmn; f = fn;
                 }
             }
             __syncwarp();
@@ -329,7 +356,20 @@ __global__ void __launch_bounds__(kThreadsV2, 1) composite_fwd_kernel(const FwdA
     }
 }
 
-template <int CH>
+// Warp layout per kernel (see Layout<> in composite_common.cuh).  Measured at c3 on B200: the forward is
+// fastest with 4 alpha warps x 2 blocks (feature warps get 184 registers and prefetch their weights), the
+// backward with 8 alpha warps x 1 block (its alpha side carries the gradient reductions and dominates).
+// F3DGS_BPA=1|2 overrides both for experiments.
+int composite_layout_bpa(int default_bpa) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("F3DGS_BPA");
+        forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+    }
+    return forced ? forced : default_bpa;
+}
+
+template <int CH, int BPA>
 static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                 const SplatRec* rec, const float* features, const float* bg, float* final_T,
                                 uint32_t* n_contrib, float* out_color, float* out_feature, float* out_depth,
@@ -338,7 +378,7 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<CH, BPA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -362,26 +402,26 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms > 0 ? num_sms : 148);
-    composite_fwd_kernel<CH><<<grid, kThreadsV2, smem, s>>>(a);
+    composite_fwd_kernel<CH, BPA><<<grid, Layout<BPA>::kThreads, smem, s>>>(a);
     g_launches++;
     return cudaGetLastError();
 }
+
+#define F3DGS_FWD_DISPATCH(CHV)                                                                                   \
+    (composite_layout_bpa(2) == 2                                                                                \
+         ? launch_fwd_t<CHV, 2>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,       \
+                                out_feature, out_depth, work_counter, s)                                        \
+         : launch_fwd_t<CHV, 1>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,       \
+                                out_feature, out_depth, work_counter, s))
 
 cudaError_t launch_composite_fwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                  const SplatRec* rec, const float* features, const float* bg,
                                  float* final_T, uint32_t* n_contrib, float* out_color,
                                  float* out_feature, float* out_depth, int* work_counter, cudaStream_t s) {
-    if (vp.C == 0)
-        return launch_fwd_t<0>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,
-                               out_feature, out_depth, work_counter, s);
-    if (vp.C <= 32)
-        return launch_fwd_t<32>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,
-                                out_feature, out_depth, work_counter, s);
-    if (vp.C <= 64)
-        return launch_fwd_t<64>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,
-                                out_feature, out_depth, work_counter, s);
-    return launch_fwd_t<128>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,
-                             out_feature, out_depth, work_counter, s);
+    if (vp.C == 0) return F3DGS_FWD_DISPATCH(0);
+    if (vp.C <= 32) return F3DGS_FWD_DISPATCH(32);
+    if (vp.C <= 64) return F3DGS_FWD_DISPATCH(64);
+    return F3DGS_FWD_DISPATCH(128);
 }
 
 }  // namespace f3dgs
