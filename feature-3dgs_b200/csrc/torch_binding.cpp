@@ -65,9 +65,10 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
     const auto dev = means3D.device();
     const int P = means3D.size(0);
     const int H = image_height, W = image_width;
-    const bool has_feat = semantic_feature.defined() && semantic_feature.numel() > 0;
-    const int C = has_feat ? (int)semantic_feature.size(-1) : 0;
-    if (has_feat) TORCH_CHECK(semantic_feature.numel() == (int64_t)P * C, "semantic_feature must be [P, 1, C]");
+    // feature width = last dimension (also for an empty cloud [0,1,C]); an absent feature input is a 0-element 1-D tensor
+    const int C = (semantic_feature.defined() && semantic_feature.dim() >= 1) ? (int)semantic_feature.size(-1) : 0;
+    TORCH_CHECK(!semantic_feature.defined() || semantic_feature.numel() == (int64_t)P * C,
+                "semantic_feature must be [P, 1, C]");
 
     auto float_opts = means3D.options().dtype(torch::kFloat32);
     // every element of the outputs is written by the composite kernel, so no zero-fill pass
@@ -125,9 +126,8 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
     const int W = dL_dout_color.size(2);
     int M = 0;
     if (sh.defined() && sh.numel() != 0) M = sh.size(1);
-    const bool has_feat = semantic_feature.defined() && semantic_feature.numel() > 0;
-    const int C = has_feat ? (int)semantic_feature.size(-1) : 0;
-    const int64_t mid = has_feat && semantic_feature.dim() == 3 ? semantic_feature.size(1) : 1;
+    const int C = (semantic_feature.defined() && semantic_feature.dim() >= 1) ? (int)semantic_feature.size(-1) : 0;
+    const int64_t mid = (semantic_feature.defined() && semantic_feature.dim() == 3) ? semantic_feature.size(1) : 1;
 
     auto o = means3D.options().dtype(torch::kFloat32);
     torch::Tensor dL_dmeans3D = torch::zeros({P, 3}, o);

@@ -26,6 +26,10 @@ CONFIGS: Dict[str, dict] = {
     "c3": dict(P=1_000_000, W=1920, H=1080, C=128, sh_degree=3, views=1),
     "c4": dict(P=1_000_000, W=1920, H=1080, C=256, sh_degree=3, views=64),
     "c5": dict(P=5_000_000, W=3840, H=2160, C=64, sh_degree=3, views=1),
+    # analysis variants of c3 (same cloud and camera, other feature widths)
+    "c3_C0": dict(P=1_000_000, W=1920, H=1080, C=0, sh_degree=3, views=1),
+    "c3_C32": dict(P=1_000_000, W=1920, H=1080, C=32, sh_degree=3, views=1),
+    "c3_C64": dict(P=1_000_000, W=1920, H=1080, C=64, sh_degree=3, views=1),
     # small cases for parity tests / golden fixtures
     "tiny": dict(P=600, W=80, H=56, C=8, sh_degree=3, views=1),
     "small": dict(P=4000, W=160, H=112, C=16, sh_degree=2, views=1),
@@ -123,7 +127,7 @@ def make_config(name: str, seed: int = None, views: int = None) -> Scene:
     if views is not None:
         cfg["views"] = views
     if seed is None:
-        seed = list(CONFIGS).index(name) + 1
+        seed = 3 if name.startswith("c3_") else list(CONFIGS).index(name) + 1
     return make_scene(seed=seed, **cfg)
 
 
