@@ -22,6 +22,8 @@ CU = ["api.cu", "preprocess.cu", "binning.cu", "composite_fwd.cu", "composite_bw
 HDRS = ["common.cuh", "kernels.h", "composite_common.cuh", os.path.join(ROOT, "include", "f3dgs_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+if os.environ.get("F3DGS_TIMING_BUILD") == "1":  # per-role cycle counters in the composite kernels (debug builds only)
+    NVCC_FLAGS.append("-DF3DGS_TIMING_BUILD=1")
 
 
 def _run(cmd, log=None):

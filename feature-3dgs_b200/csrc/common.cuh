@@ -84,9 +84,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// The whole wait loop is one asm block: written as a C loop the compiler re-materialises the barrier address (S2R
+// SR_CgaCtaId, LEA, ...) inside it, 17 instructions per poll, and waiting warps then take a quarter of the SM's issue
+// slots from the warps they wait for (ncu source counters, profiles/r01d_*).  Here a poll is TRYWAIT + NANOSLEEP + BRA.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "F3DGS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra F3DGS_DONE_%=;\n\t"
+        "bra F3DGS_WAIT_%=;\n\t"
+        "F3DGS_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
@@ -98,10 +108,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---------------------------------------------------------------- vector global access
 __device__ __forceinline__ void st_na_f4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
+                 : "memory");
+}
+// 256-bit store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_na_f8(float* p, float4 a, float4 b) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y),
+                 "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
                  : "memory");
 }
 __device__ __forceinline__ float4 ld_nc_f4(const float* p) {

@@ -24,10 +24,12 @@ namespace f3dgs {
 constexpr int kRedSlots = 8;
 constexpr int kRedVals = 10;
 constexpr int kRedRows = kRedSlots * kRedVals;
+constexpr int kRedStride = 36;  // floats per row: lanes park at [row][lane] (conflict-free), rows are summed with
+                                // LDS.128 (quarter-warp wavefronts: rows r..r+7 start 4 banks apart -> conflict-free)
 
 struct alignas(128) BwdSmem {
     RingV2<0> ring;
-    float red[kBlocksPerTile][kRedRows][33];
+    float red[kBlocksPerTile][kRedRows][kRedStride];
     uint32_t red_gid[kBlocksPerTile][kRedSlots];
 };
 
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
     if (warp < L::kFeatWarp0) {
         reg_dec<L::kRegsAlpha>();
         const int a = warp - kAlphaWarp0;  // owns blocks BPA*a .. BPA*a + BPA-1
-        float(*red)[33] = sm.red[a];
+        float(*red)[kRedStride] = sm.red[a];
         uint32_t* red_gid = sm.red_gid[a];
         uint32_t nslots = 0;  // warp-uniform; rows of both blocks share the scratch
         int s = 0, j = 0;
@@ -96,12 +98,14 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                 const int slot = r % kRedSlots, v = r / kRedSlots;
                 if (slot < (int)nslots) {
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    const float4* row = reinterpret_cast<const float4*>(red[r]);
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj += 4) {
-                        s0 += red[r][jj];
-                        s1 += red[r][jj + 1];
-                        s2 += red[r][jj + 2];
-                        s3 += red[r][jj + 3];
+                    for (int jj = 0; jj < 8; jj++) {
+                        const float4 q = row[jj];
+                        s0 += q.x;
+                        s1 += q.y;
+                        s2 += q.z;
+                        s3 += q.w;
                     }
                     const float sum = (s0 + s1) + (s2 + s3);
                     const uint32_t gid = red_gid[slot];
@@ -212,8 +216,11 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                             if (contrib) {
                                 const float4 r1 = st.rec1[k];
                                 const float4 r2 = st.rec2[k];
-                                const float one_m_a = 1.f - alpha;
-                                p.T = p.T / one_m_a;
+                                // 1/(1-alpha), 1-alpha in [0.01, 1]: one MUFU.RCP (<= 1 ulp) serves both the T unwind and
+                                // the background term, where the reference divides twice (backward.cu:541,583); the
+                                // unwound T differs from the reference's by a few ulp after a whole tile list.
+                                const float inv_1ma = rcp_approx(1.f - alpha);
+                                p.T = p.T * inv_1ma;
                                 wgt = alpha * p.T;
                                 float dL_dalpha;
                                 p.ar0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.ar0; p.lc0 = r2.x;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                                 dL_dalpha += (r2.w - p.accum_depth) * p.dLd;
                                 dL_dalpha *= p.T;
                                 p.last_alpha = alpha;
-                                dL_dalpha += (-p.T_final / one_m_a) * p.bg_dot;
+                                dL_dalpha += (-p.T_final * inv_1ma) * p.bg_dot;
                                 const float Gs = Gv[u], dx = dxv[u], dy = dyv[u];
                                 const float dL_dG = r1.w * dL_dalpha;
                                 const float gdx = Gs * dx, gdy = Gs * dy;

@@ -50,7 +50,9 @@ struct Layout {
 constexpr int kStageEntries = 32;
 constexpr int kStages = 4;
 constexpr int kWSlots = 2;
-constexpr int kDoneSlots = 8;       // > kStages: the producer is never further ahead than that
+constexpr int kDoneSlots = 8;       // > kStages: the producer is never further ahead than that.  Slots are indexed by the
+                                    // CTA's own work sequence number, NOT by the work id: ids come from a global
+                                    // atomic counter, so two items in flight in one CTA can be congruent mod 8.
 
 template <int CH>
 struct alignas(128) Stage {
@@ -64,6 +66,7 @@ struct alignas(128) Stage {
     uint32_t last;                                // 1 = last stage of this work item
     uint32_t first;                               // 1 = first stage of this work item
     int32_t work;                                 // work item (tile * chunks + chunk); < 0: no more work
+    uint32_t done_slot;                           // index into RingV2::done_mask for this work item
 };
 
 struct alignas(128) WSlot {
@@ -147,10 +150,12 @@ __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerAr
     uint32_t empty_parity = 1;  // fresh barrier: waiting on parity 1 falls through
     mbar_wait(&ring.empty[0], empty_parity);
 
+    uint32_t seq = 0;  // work items this CTA has started
     auto publish = [&](uint32_t n, uint32_t last, uint32_t first, int work, uint32_t row_bytes) {
         __syncwarp();
         if (lane == 0) {
             Stage<CH>& st = ring.stage[s];
+            st.done_slot = seq % kDoneSlots;
             st.n = n;
             st.last = last;
             st.first = first;
@@ -200,7 +205,8 @@ __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerAr
         const int chunk_off = chunk * CH;
         const int row_floats = (CH > 0 && pa.features != nullptr) ? min(CH, pa.C - chunk_off) : 0;
         const uint32_t row_bytes = (uint32_t)row_floats * 4u;
-        uint32_t* done = &ring.done_mask[work % kDoneSlots];
+        seq++;
+        uint32_t* done = &ring.done_mask[seq % kDoneSlots];
         if (lane == 0) *reinterpret_cast<volatile uint32_t*>(done) = 0;
         __syncwarp();
 

@@ -17,11 +17,22 @@
 //                  channels (= 128 accumulators per lane at CH = 128) live in registers.
 // Channel counts above 128 are split into chunks of 128 (extra work items); chunk 0 also writes
 // colour, depth, final_T and n_contrib.
+#include <cstdio>
 #include <cstdlib>
 
 #include "composite_common.cuh"
 
 namespace f3dgs {
+
+#ifndef F3DGS_TIMING_BUILD
+#define F3DGS_TIMING_BUILD 0   // build.py sets 1 when env F3DGS_TIMING_BUILD=1: per-role cycle counters (see tools/stage_times.py)
+#endif
+#ifndef F3DGS_FWD_A1
+#define F3DGS_FWD_A1 64
+#define F3DGS_FWD_F1 152
+#endif
+static constexpr bool kTiming = F3DGS_TIMING_BUILD != 0;
+#define TICK() ((kTiming && args.dbg) ? clock64() : 0ll)
 
 struct FwdArgs {
     ProducerArgs pa;
@@ -32,6 +43,18 @@ struct FwdArgs {
     float* out_feature;
     float* out_depth;
     int vec_store;
+    long long* dbg;  // F3DGS_TIMING=1: per-warp cycle counters [cta][warp][8], else nullptr
+};
+
+// Forward register budget.  BPA == 1 (20 warps, launched at 96 regs/thread = 61440 in the CTA pool):
+// 4x32x40 + 8x32x64 + 8x32x152 = 60416, feature warps run the sparse quad loop.  The alternative 40/48/168 with the
+// dense hoisted loop (-DF3DGS_FWD_A1=48 -DF3DGS_FWD_F1=168) measured 2.37 ms vs 2.19 ms at c3: the extra FFMA issue
+// of the dense loop takes more from the alpha warps sharing the SMSP than the hoisted loads give back.
+template <int BPA>
+struct FwdLayout : Layout<BPA> {
+    static constexpr int kRegsAlpha = BPA == 2 ? 104 : F3DGS_FWD_A1;
+    static constexpr int kRegsFeature = BPA == 2 ? 184 : F3DGS_FWD_F1;
+    static constexpr bool kPrefetchW = BPA == 2 || F3DGS_FWD_F1 >= 168;
 };
 
 template <int CH, int BPA>
@@ -42,14 +65,18 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
     const size_t HW = (size_t)H * W;
 
-    using L = Layout<BPA>;
+    using L = FwdLayout<BPA>;
     ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
     __syncthreads();
 
     // ======================================================================== producer group
     if (warp < kAlphaWarp0) {
         reg_dec<L::kRegsProducer>();
-        if (warp == kProducerWarp) producer_loop<CH, false>(ring, args.pa);
+        if (warp == kProducerWarp) {
+            const long long t0 = TICK();
+            producer_loop<CH, false>(ring, args.pa);
+            if (kTiming && args.dbg && (threadIdx.x & 31) == 0) args.dbg[(blockIdx.x * 32 + warp) * 8 + 0] = clock64() - t0;
+        }
         return;
     }
 
@@ -68,8 +95,10 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
             T[bi] = 1.f; Cr[bi] = Cg[bi] = Cb[bi] = Dp[bi] = 0.f; pxf[bi] = pyf[bi] = fbx0[bi] = fby0[bi] = 0.f;
             last_contrib[bi] = 0; px[bi] = py[bi] = 0; done[bi] = true; inside[bi] = false; blk_done[bi] = true;
         }
+        long long tA_full = 0, tA_wempty = 0, tA_total = TICK(), nA_stage = 0, nA_hits = 0;
         for (;;) {
-            mbar_wait(&ring.full[s], parity);
+            { const long long t_ = TICK(); mbar_wait(&ring.full[s], parity); tA_full += TICK() - t_; }
+            nA_stage++;
             Stage<CH>& st = ring.stage[s];
             const uint32_t n = st.n, last = st.last, first = st.first;
             const int work = st.work;
@@ -91,14 +120,129 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                     last_contrib[bi] = 0;
                     done[bi] = !inside[bi];
                     blk_done[bi] = __all_sync(0xffffffffu, done[bi]);
-                    if (blk_done[bi] && lane == 0) atomicOr(&ring.done_mask[work % kDoneSlots], 1u << b);
+                    if (blk_done[bi] && lane == 0) atomicOr(&ring.done_mask[st.done_slot], 1u << b);
                 }
             }
+            if constexpr (BPA == 2) {
+                // Two blocks per alpha warp, advanced in lock-step.  One trip takes up to two hits of each block:
+                // all operand loads first, then the four alpha evaluations written "transposed" (one operation
+                // across the four instances at a time) so their LDS -> FFMA -> MUFU.EX2 chains overlap, then the
+                // two blocks' T recurrences as two independent dependency chains.
+                WSlot* wsl[2] = {&ring.ws[2 * a][j], &ring.ws[2 * a + 1][j]};
+                if (CH > 0) {
+                    const long long t_ = TICK();
+                    mbar_wait(&ring.wempty[2 * a][j], wparity);
+                    mbar_wait(&ring.wempty[2 * a + 1][j], wparity);
+                    tA_wempty += TICK() - t_;
+                }
+                uint32_t kmv[2] = {0u, 0u};
+                if (n > 0 && !(blk_done[0] && blk_done[1])) {
+                    bool h0 = false, h1 = false;
+                    if (lane < n) {
+                        const float4 r0 = st.rec0[lane];
+                        const bool hy = (r0.y + r0.w >= fby0[0]) && (r0.y - r0.w <= fby0[0] + 3.f);  // same pixel rows
+                        h0 = hy && (r0.x + r0.z >= fbx0[0]) && (r0.x - r0.z <= fbx0[0] + 7.f);
+                        h1 = hy && (r0.x + r0.z >= fbx0[1]) && (r0.x - r0.z <= fbx0[1] + 7.f);
+                    }
+                    uint32_t amv[2];
+                    amv[0] = blk_done[0] ? 0u : __ballot_sync(0xffffffffu, h0);
+                    amv[1] = blk_done[1] ? 0u : __ballot_sync(0xffffffffu, h1);
+                    nA_hits += __popc(amv[0]) + __popc(amv[1]);
+                    while (amv[0] | amv[1]) {
+                        int kk[4];   // e = 2*u + bi
+                        bool vk[4];
+#pragma unroll
+                        for (int u = 0; u < 2; u++)
+#pragma unroll
+                            for (int bi = 0; bi < 2; bi++) {
+                                const int e = 2 * u + bi;
+                                vk[e] = amv[bi] != 0;
+                                kk[e] = vk[e] ? (__ffs(amv[bi]) - 1) : 0;
+                                amv[bi] &= amv[bi] - 1;
+                            }
+                        float2 xy[4];
+                        float4 co[4], r2[4];
+                        uint32_t lp[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            xy[e] = *reinterpret_cast<const float2*>(&st.rec0[kk[e]]);
+                            co[e] = st.rec1[kk[e]];
+                            r2[e] = st.rec2[kk[e]];
+                            lp[e] = st.listpos[kk[e]];
+                        }
+                        asm volatile("" ::: "memory");
+                        float dx[4], dy[4], pw[4], av[4], al[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) { dx[e] = xy[e].x - pxf[e & 1]; dy[e] = xy[e].y - pyf[e & 1]; }
+                        // same expression trees as reference forward.cu:340-351 (see common.cuh)
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            pw[e] = -0.5f * (co[e].x * dx[e] * dx[e] + co[e].z * dy[e] * dy[e]) - co[e].y * dx[e] * dy[e];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) av[e] = fminf(0.99f, co[e].w * expf(pw[e]));
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            al[e] = (vk[e] && !(pw[e] > 0.0f) && !(av[e] < 1.0f / 255.0f)) ? av[e] : 0.f;
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            float wgt[2];
+                            bool blend[2];
+#pragma unroll
+                            for (int bi = 0; bi < 2; bi++) {
+                                const int e = 2 * u + bi;
+                                const float alpha = al[e];
+                                const float test_T = T[bi] * (1 - alpha);
+                                const bool act = !done[bi] && alpha > 0.f;
+                                const bool stop = act && (test_T < 0.0001f);  // reference: done = true, not blended
+                                blend[bi] = act && !stop;
+                                done[bi] = done[bi] || stop;
+                                wgt[bi] = blend[bi] ? alpha * T[bi] : 0.f;
+                                const float nCr = Cr[bi] + r2[e].x * alpha * T[bi];  // reference forward.cu:362-368
+                                const float nCg = Cg[bi] + r2[e].y * alpha * T[bi];
+                                const float nCb = Cb[bi] + r2[e].z * alpha * T[bi];
+                                const float nDp = Dp[bi] + r2[e].w * (alpha * T[bi]);
+                                Cr[bi] = blend[bi] ? nCr : Cr[bi];
+                                Cg[bi] = blend[bi] ? nCg : Cg[bi];
+                                Cb[bi] = blend[bi] ? nCb : Cb[bi];
+                                Dp[bi] = blend[bi] ? nDp : Dp[bi];
+                                T[bi] = blend[bi] ? test_T : T[bi];
+                                last_contrib[bi] = blend[bi] ? lp[e] : last_contrib[bi];
+                            }
+#pragma unroll
+                            for (int bi = 0; bi < 2; bi++) {
+                                const int e = 2 * u + bi;
+                                const uint32_t pm = __ballot_sync(0xffffffffu, blend[bi]);
+                                if (CH > 0 && vk[e]) {  // warp-uniform
+                                    wsl[bi]->w[kk[e]][lane] = wgt[bi];
+                                    if (lane == 0) wsl[bi]->pm[kk[e]] = pm;
+                                    kmv[bi] |= (pm ? 1u : 0u) << kk[e];
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int bi = 0; bi < 2; bi++)
+                        if (!blk_done[bi] && __all_sync(0xffffffffu, done[bi])) {
+                            blk_done[bi] = true;
+                            if (lane == 0) atomicOr(&ring.done_mask[st.done_slot], 1u << (2 * a + bi));
+                        }
+                }
+                if (CH > 0) {
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int bi = 0; bi < 2; bi++) {
+                            wsl[bi]->km = kmv[bi]; wsl[bi]->last = last; wsl[bi]->first = first; wsl[bi]->work = work;
+                            mbar_arrive(&ring.wfull[2 * a + bi][j]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int bi = 0; bi < BPA; bi++) {
                 const int b = BPA * a + bi;
                 WSlot* ws = &ring.ws[b][j];
-                if (CH > 0) mbar_wait(&ring.wempty[b][j], wparity);
+                if (CH > 0) { const long long t_ = TICK(); mbar_wait(&ring.wempty[b][j], wparity); tA_wempty += TICK() - t_; }
                 uint32_t km = 0;
                 if (!blk_done[bi] && n > 0) {
                     bool hit = false;
@@ -108,6 +252,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                               (r0.y + r0.w >= fby0[bi]) && (r0.y - r0.w <= fby0[bi] + 3.f);
                     }
                     uint32_t am = __ballot_sync(0xffffffffu, hit);
+                    nA_hits += __popc(am);
                     while (am) {
                         // Up to 4 instances per trip.  Everything is branch-free so that the four alpha
                         // evaluations (LDS -> power -> expf) interleave in the pipeline; only the short
@@ -163,7 +308,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                     }
                     if (__all_sync(0xffffffffu, done[bi])) {
                         blk_done[bi] = true;
-                        if (lane == 0) atomicOr(&ring.done_mask[work % kDoneSlots], 1u << b);
+                        if (lane == 0) atomicOr(&ring.done_mask[st.done_slot], 1u << b);
                     }
                 }
                 if (CH > 0) {
@@ -176,6 +321,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                         mbar_arrive(&ring.wfull[b][j]);
                     }
                 }
+            }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[s]);
@@ -194,6 +340,10 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
             }
             if (++s == kStages) { s = 0; parity ^= 1; }
             if (CH > 0 && ++j == kWSlots) { j = 0; wparity ^= 1; }
+        }
+        if (kTiming && args.dbg && lane == 0) {
+            long long* d = args.dbg + (blockIdx.x * 32 + warp) * 8;
+            d[0] = clock64() - tA_total; d[1] = tA_full; d[2] = tA_wempty; d[3] = nA_stage; d[4] = nA_hits;
         }
         if (CH > 0) {  // tell the feature warps of these blocks that the work is over
 #pragma unroll
@@ -228,51 +378,40 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                 for (int c = 0; c < 4; c++) acc[q][i][c] = 0.f;
         int s = 0, j = 0;
         uint32_t parity = 0, wparity = 0;
+        long long tF_wfull = 0, tF_full = 0, tF_epi = 0, tF_total = TICK(), nF_k = 0;
         for (;;) {
-            mbar_wait(&ring.wfull[b][j], wparity);
+            { const long long t_ = TICK(); mbar_wait(&ring.wfull[b][j], wparity); tF_wfull += TICK() - t_; }
             const WSlot& ws = ring.ws[b][j];
             const int work = ws.work;
             if (work < 0) break;
             uint32_t km = ws.km;
             const uint32_t last = ws.last;
-            mbar_wait(&ring.full[s], parity);  // feature rows of this stage have landed
+            { const long long t_ = TICK(); mbar_wait(&ring.full[s], parity); tF_full += TICK() - t_; }  // feature rows landed
+            nF_k += __popc(km);
             const Stage<CH>& st = ring.stage[s];
             if (L::kPrefetchW) {
-                if (km) {
-                    // software pipeline over the blended instances: the next instance's mask and feature
-                    // float4 are fetched while the current one is being accumulated; all weight quads of
-                    // the current instance are loaded up front so no LDS sits between the FFMA blocks
-                    int k = __ffs(km) - 1;
+                // 184-register layout: dense over the block with every operand of an instance fetched before its
+                // 128 FFMAs (the compiler barrier keeps the nine LDS.128 ahead of the FFMA stream), so the FMA pipe
+                // sees one uninterrupted run per instance.  Pixels that skipped the instance carry w = 0.
+                while (km) {
+                    const int k = __ffs(km) - 1;
                     km &= km - 1;
-                    uint32_t pm = ws.pm[k];
-                    float4 f = *reinterpret_cast<const float4*>(&st.feat[k][cl * 4]);
-                    for (;;) {
-                        float4 w4[NQ];
+                    const float4 f = *reinterpret_cast<const float4*>(&st.feat[k][cl * 4]);
+                    float4 w4[NQ];
 #pragma unroll
-                        for (int qi = 0; qi < NQ; qi++)
-                            w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
-                        const bool more = km != 0;
-                        const int kn = more ? (__ffs(km) - 1) : k;
-                        km &= km - 1;
-                        const uint32_t pmn = ws.pm[kn];
-                        const float4 fn = *reinterpret_cast<const float4*>(&st.feat[kn][cl * 4]);
+                    for (int qi = 0; qi < NQ; qi++)
+                        w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
+                    asm volatile("" ::: "memory");
 #pragma unroll
-                        for (int qi = 0; qi < NQ; qi++) {
-                            const int q = qi * G + grp;
-                            if ((pm >> (4 * q)) & 0xFu) {
-                                // a pixel that skipped this instance stored w = 0: adds exactly 0
-                                const float wv[4] = {w4[qi].x, w4[qi].y, w4[qi].z, w4[qi].w};
+                    for (int qi = 0; qi < NQ; qi++) {
+                        const float wv[4] = {w4[qi].x, w4[qi].y, w4[qi].z, w4[qi].w};
 #pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    acc[qi][i][0] = fmaf(f.x, wv[i], acc[qi][i][0]);
-                                    acc[qi][i][1] = fmaf(f.y, wv[i], acc[qi][i][1]);
-                                    acc[qi][i][2] = fmaf(f.z, wv[i], acc[qi][i][2]);
-                                    acc[qi][i][3] = fmaf(f.w, wv[i], acc[qi][i][3]);
-                                }
-                            }
+                        for (int i = 0; i < 4; i++) {
+                            acc[qi][i][0] = fmaf(f.x, wv[i], acc[qi][i][0]);
+                            acc[qi][i][1] = fmaf(f.y, wv[i], acc[qi][i][1]);
+                            acc[qi][i][2] = fmaf(f.z, wv[i], acc[qi][i][2]);
+                            acc[qi][i][3] = fmaf(f.w, wv[i], acc[qi][i][3]);
                         }
-                        if (!more) break;
-                        k = kn; pm = pmn; f = fn;
                     }
                 }
             } else {
@@ -303,6 +442,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                 mbar_arrive(&ring.wempty[b][j]);
                 mbar_arrive(&ring.empty[s]);
             }
+            const long long tE_ = TICK();
             if (last) {
                 // ---- epilogue of this work item: write the block's 32 pixels x CH channels, reset
                 const int tile = work / args.pa.chunks, chunk = work - tile * args.pa.chunks;
@@ -313,8 +453,21 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                     const int ch = chunk * CH + cl * 4 + c;
                     if (ch < C) {
                         float* plane = args.out_feature + (size_t)ch * HW;
-                        if (G == 1 && args.vec_store) {
-                            // lane holds all 8 quads: rows of 8 pixels -> two 128-bit stores per row
+                        if (G == 1 && (args.vec_store & 2) && bx0 + 8 <= W) {
+                            // lane holds all 8 quads: one 256-bit store = a full 32-byte sector per 8-pixel row
+#pragma unroll
+                            for (int y = 0; y < 4; y++) {
+                                const int yy = by0 + y;
+                                if (yy >= H) continue;
+                                const int qa = (y >> 1) * 4, i0 = (y & 1) * 2;
+                                st_na_f8(plane + (size_t)yy * W + bx0,
+                                         make_float4(acc[qa % NQ][i0][c], acc[qa % NQ][i0 + 1][c],
+                                                     acc[(qa + 1) % NQ][i0][c], acc[(qa + 1) % NQ][i0 + 1][c]),
+                                         make_float4(acc[(qa + 2) % NQ][i0][c], acc[(qa + 2) % NQ][i0 + 1][c],
+                                                     acc[(qa + 3) % NQ][i0][c], acc[(qa + 3) % NQ][i0 + 1][c]));
+                            }
+                        } else if (G == 1 && (args.vec_store & 1)) {
+                            // rows of 8 pixels -> two 128-bit stores per row
 #pragma unroll
                             for (int y = 0; y < 4; y++) {
                                 const int yy = by0 + y;
@@ -350,15 +503,20 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
 #pragma unroll
                         for (int c = 0; c < 4; c++) acc[q][i][c] = 0.f;
             }
+            tF_epi += TICK() - tE_;
             if (++s == kStages) { s = 0; parity ^= 1; }
             if (++j == kWSlots) { j = 0; wparity ^= 1; }
+        }
+        if (kTiming && args.dbg && lane == 0) {
+            long long* d = args.dbg + (blockIdx.x * 32 + warp) * 8;
+            d[0] = clock64() - tF_total; d[1] = tF_wfull; d[2] = tF_full; d[3] = tF_epi; d[4] = nF_k;
         }
     }
 }
 
-// Warp layout per kernel (see Layout<> in composite_common.cuh).  Measured at c3 on B200: the forward is
-// fastest with 4 alpha warps x 2 blocks (feature warps get 184 registers and prefetch their weights), the
-// backward with 8 alpha warps x 1 block (its alpha side carries the gradient reductions and dominates).
+// Warp layout per kernel (see Layout<> in composite_common.cuh).  Measured at c3 on B200 (round 1, final kernels):
+// forward 2.19 ms with 8 alpha warps x 1 block vs 2.41 ms with 4 alpha warps x 2 blocks (184-register feature
+// warps running the dense hoisted loop); backward 4.2 ms vs 5.5 ms.  Both default to 8 x 1.
 // F3DGS_BPA=1|2 overrides both for experiments.
 int composite_layout_bpa(int default_bpa) {
     static int forced = -1;
@@ -399,16 +557,37 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib;
     a.out_color = out_color; a.out_feature = out_feature; a.out_depth = out_depth;
     a.vec_store = (vp.W % 4 == 0 && (reinterpret_cast<uintptr_t>(out_feature) & 15) == 0) ? 1 : 0;
+    if (vp.W % 8 == 0 && (reinterpret_cast<uintptr_t>(out_feature) & 31) == 0) a.vec_store |= 2;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms > 0 ? num_sms : 148);
+    static long long* dbg = nullptr;
+    const bool timing = getenv("F3DGS_TIMING") != nullptr;  // debug aid: per-role cycle breakdown on stderr
+    if (timing && !dbg) cudaMalloc(&dbg, 256 * 32 * 8 * sizeof(long long));
+    a.dbg = (kTiming && timing) ? dbg : nullptr;
+    if (timing) cudaMemsetAsync(dbg, 0, 256 * 32 * 8 * sizeof(long long), s);
     composite_fwd_kernel<CH, BPA><<<grid, Layout<BPA>::kThreads, smem, s>>>(a);
     g_launches++;
+    if (timing) {
+        static long long host[256 * 32 * 8];
+        cudaMemcpyAsync(host, dbg, sizeof(host), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        const int nA = Layout<BPA>::kAlphaWarps, f0 = Layout<BPA>::kFeatWarp0;
+        double prod = 0, A[5] = {0, 0, 0, 0, 0}, F[5] = {0, 0, 0, 0, 0};
+        for (int c = 0; c < grid; c++) {
+            prod += host[(c * 32 + 0) * 8];
+            for (int w = 0; w < nA; w++) for (int i = 0; i < 5; i++) A[i] += host[(c * 32 + kAlphaWarp0 + w) * 8 + i];
+            for (int w = 0; w < 8; w++) for (int i = 0; i < 5; i++) F[i] += host[(c * 32 + f0 + w) * 8 + i];
+        }
+        fprintf(stderr, "[f3dgs timing fwd CH=%d BPA=%d] per-warp mean cycles: producer %.0f | alpha total %.0f wait_full %.0f wait_wempty %.0f stages %.0f hits %.0f | feature total %.0f wait_wfull %.0f wait_full %.0f epilogue %.0f k %.0f\n",
+                CH, BPA, prod / grid, A[0] / (grid * nA), A[1] / (grid * nA), A[2] / (grid * nA), A[3] / (grid * nA), A[4] / (grid * nA),
+                F[0] / (grid * 8), F[1] / (grid * 8), F[2] / (grid * 8), F[3] / (grid * 8), F[4] / (grid * 8));
+    }
     return cudaGetLastError();
 }
 
 #define F3DGS_FWD_DISPATCH(CHV)                                                                                   \
-    (composite_layout_bpa(2) == 2                                                                                \
+    (composite_layout_bpa(1) == 2                                                                                \
          ? launch_fwd_t<CHV, 2>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,       \
                                 out_feature, out_depth, work_counter, s)                                        \
          : launch_fwd_t<CHV, 1>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,       \

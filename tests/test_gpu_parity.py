@@ -226,6 +226,43 @@ def test_runs_on_the_current_stream_and_is_deterministic_forward():
         assert np.array_equal(a[k], b[k]), k
 
 
+def test_forward_bit_identical_over_many_runs_c2():
+    """Race regression (round 1): the persistent composite hands tiles out through a global atomic counter, so which
+    tiles share a CTA - and how far its producer warp runs ahead - changes from run to run.  The forward has no
+    atomics in its data path, so its outputs must not: 40 runs of config 2 (300k Gaussians, 800x800, C=16; this
+    caught early-termination flags of two in-flight tiles aliasing) and the backward must agree within a fraction
+    of the parity tolerance (its float atomics may reorder)."""
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+    sc = scenegen.make_config("c2")
+    cam = sc.cameras[0]
+    t = scenegen.to_torch(sc, "cuda", requires_grad=True)
+    rs = GaussianRasterizationSettings(**scenegen.settings_kwargs(sc, cam, "cuda"))
+    gc, gf, gd = [torch.from_numpy(g).cuda() for g in scenegen.upstream_grads(cam.image_height, cam.image_width, sc.C)]
+    base = gbase = None
+    for it in range(40):
+        m2 = torch.zeros_like(t["means3D"], requires_grad=True)
+        color, feat, radii, depth = GaussianRasterizer(rs)(
+            means3D=t["means3D"], means2D=m2, opacities=t["opacities"], shs=t["shs"],
+            semantic_feature=t["semantic_feature"], scales=t["scales"], rotations=t["rotations"])
+        torch.autograd.backward([color, depth, feat], [gc, gd, gf])
+        cur = [color.detach().clone(), feat.detach().clone(), depth.detach().clone(), radii.clone()]
+        g = {k: t[k].grad.clone() for k in t if t[k].grad is not None}
+        g["means2D"] = m2.grad.clone()
+        for k in t:
+            t[k].grad = None
+        if base is None:
+            base, gbase = cur, g
+            continue
+        for a, b, k in zip(cur, base, ("color", "feature_map", "depth", "radii")):
+            assert torch.equal(a, b), (it, k, int((a != b).sum()))
+        for k in g:
+            b = gbase[k].double()
+            tol = parity.RTOL * b.abs() + parity.GRAD_ATOL_REL * b.abs().max()
+            assert float(((g[k].double() - b).abs() / tol).max()) <= 0.5, (it, k)
+
+
 def test_mark_visible_matches_oracle():
     import torch
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
