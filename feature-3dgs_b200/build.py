@@ -22,6 +22,7 @@ CU = ["api.cu", "preprocess.cu", "binning.cu", "composite_fwd.cu", "composite_bw
 HDRS = ["common.cuh", "kernels.h", "composite_common.cuh", os.path.join(ROOT, "include", "f3dgs_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += os.environ.get("F3DGS_EXTRA_NVCC_FLAGS", "").split()  # experiments: -DF3DGS_STAGES=6 -DF3DGS_WSLOTS=3 ...
 if os.environ.get("F3DGS_TIMING_BUILD") == "1":  # per-role cycle counters in the composite kernels (debug builds only)
     NVCC_FLAGS.append("-DF3DGS_TIMING_BUILD=1")
 

@@ -48,8 +48,14 @@ struct Layout {
     static constexpr bool kPrefetchW = BPA == 2;  // room to hold all weight quads + the next instance's row
 };
 constexpr int kStageEntries = 32;
-constexpr int kStages = 4;
-constexpr int kWSlots = 2;
+#ifndef F3DGS_STAGES
+#define F3DGS_STAGES 6
+#endif
+#ifndef F3DGS_WSLOTS
+#define F3DGS_WSLOTS 2
+#endif
+constexpr int kStages = F3DGS_STAGES;
+constexpr int kWSlots = F3DGS_WSLOTS;
 constexpr int kDoneSlots = 8;       // > kStages: the producer is never further ahead than that.  Slots are indexed by the
                                     // CTA's own work sequence number, NOT by the work id: ids come from a global
                                     // atomic counter, so two items in flight in one CTA can be congruent mod 8.
@@ -84,6 +90,7 @@ struct alignas(128) RingV2 {
     WSlot ws[kBlocksPerTile][kWSlots];
     uint64_t full[kStages];
     uint64_t empty[kStages];
+    uint64_t listed[kStages];  // COPYWARP: records + ids of the stage are written, its feature rows may be fetched
     uint64_t wfull[kBlocksPerTile][kWSlots];
     uint64_t wempty[kBlocksPerTile][kWSlots];
     uint32_t done_mask[kDoneSlots];  // bit b set: pixel block b of that work item needs no more instances
@@ -103,12 +110,13 @@ __device__ __forceinline__ void reg_inc() {
 }
 
 template <int CH>
-__device__ __forceinline__ void ring_init(RingV2<CH>& ring, int n_stage_consumers, bool use_w) {
+__device__ __forceinline__ void ring_init(RingV2<CH>& ring, int n_stage_consumers, bool use_w, int n_full_arrivals = 1) {
     // called by all threads before the role split; followed by __syncthreads()
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
-            mbar_init(&ring.full[s], 1);
+            mbar_init(&ring.full[s], n_full_arrivals);
             mbar_init(&ring.empty[s], n_stage_consumers);
+            mbar_init(&ring.listed[s], 1);
         }
         for (int b = 0; b < kBlocksPerTile; b++)
             for (int j = 0; j < kWSlots; j++) {
@@ -143,7 +151,12 @@ struct ProducerArgs {
 };
 
 // Producer warp: persistent over work items.  REVERSE: walk each list back to front (backward pass).
-template <int CH, bool REVERSE>
+// COPYWARP = true: the producer only walks, culls and compacts; it hands each stage's id list to copy_loop() (a
+// second warp of the producer group) through `listed[s]`, and that warp issues the stage's bulk copies.  Issuing a bulk
+// copy costs the issuing warp ~9 instructions and an R2UR round trip per row (UBLKCP takes uniform registers, so the
+// compiler serialises the lanes); with 2.4 M rows per view at config 3 that was ~45% of the producer's instructions
+// and the producer was busy 85% of the time, i.e. the pipeline's critical path (ncu source counters, round 1).
+template <int CH, bool REVERSE, bool COPYWARP = false>
 __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerArgs& pa) {
     const int lane = threadIdx.x & 31;
     int s = 0;
@@ -160,10 +173,11 @@ __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerAr
             st.last = last;
             st.first = first;
             st.work = work;
-            if (CH > 0 && pa.features != nullptr && pa.use_bulk && n > 0)
+            if (!COPYWARP && CH > 0 && pa.features != nullptr && pa.use_bulk && n > 0)
                 mbar_arrive_expect_tx(&ring.full[s], n * row_bytes);
             else
                 mbar_arrive(&ring.full[s]);
+            if (COPYWARP) mbar_arrive(&ring.listed[s]);  // release: the stage header, records and ids are visible
         }
         __syncwarp();
     };
@@ -177,10 +191,11 @@ __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerAr
     };
 
     const int num_work = pa.num_tiles * pa.chunks;
+    int pending = 0;  // lane 0: the next work item, requested one item ahead so the atomic's round trip is hidden
+    if (lane == 0) pending = atomicAdd(pa.work_counter, 1);
     for (;;) {
-        int work = 0;
-        if (lane == 0) work = atomicAdd(pa.work_counter, 1);
-        work = __shfl_sync(0xffffffffu, work, 0);
+        const int work = __shfl_sync(0xffffffffu, pending, 0);
+        if (lane == 0 && work < num_work) pending = atomicAdd(pa.work_counter, 1);
         if (work >= num_work) {
             publish(0, 1, 1, -1, 0);
             break;
@@ -223,7 +238,7 @@ __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerAr
             if (CH > 0 && row_floats > 0) {
                 const float* src = pa.features + (size_t)gid * pa.C + chunk_off;
                 if (pa.use_bulk) {
-                    bulk_g2s(&st.feat[slot][0], src, row_bytes, &ring.full[s]);
+                    if (!COPYWARP) bulk_g2s(&st.feat[slot][0], src, row_bytes, &ring.full[s]);
                 } else {
                     for (int c = 0; c < row_floats; c++) st.feat[slot][c] = __ldg(src + c);
                 }
@@ -282,6 +297,39 @@ __device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerAr
         }
         publish(fill, 1, first, work, row_bytes);
         advance();
+    }
+}
+
+// Second warp of the producer group (COPYWARP kernels): fetches the feature rows of each listed stage.
+template <int CH>
+__device__ __forceinline__ void copy_loop(RingV2<CH>& ring, const ProducerArgs& pa) {
+    const int lane = threadIdx.x & 31;
+    int s = 0;
+    uint32_t parity = 0;
+    for (;;) {
+        mbar_wait(&ring.listed[s], parity);
+        Stage<CH>& st = ring.stage[s];
+        const uint32_t n = st.n;
+        const int work = st.work;
+        if (work < 0) {
+            if (lane == 0) mbar_arrive(&ring.full[s]);
+            break;
+        }
+        const int chunk_off = (work % pa.chunks) * CH;
+        const uint32_t row_bytes = (uint32_t)min(CH, pa.C - chunk_off) * 4u;
+        if (pa.use_bulk && n > 0) {
+            if (lane == 0) mbar_arrive_expect_tx(&ring.full[s], n * row_bytes);
+            __syncwarp();
+            if (lane < n)
+                bulk_g2s(&st.feat[lane][0], pa.features + (size_t)st.gid[lane] * pa.C + chunk_off, row_bytes,
+                         &ring.full[s]);
+        } else {
+            if (lane == 0) mbar_arrive(&ring.full[s]);
+        }
+        if (++s == kStages) {
+            s = 0;
+            parity ^= 1;
+        }
     }
 }
 

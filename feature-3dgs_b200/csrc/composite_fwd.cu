@@ -27,6 +27,9 @@ namespace f3dgs {
 #ifndef F3DGS_TIMING_BUILD
 #define F3DGS_TIMING_BUILD 0   // build.py sets 1 when env F3DGS_TIMING_BUILD=1: per-role cycle counters (see tools/stage_times.py)
 #endif
+#ifndef F3DGS_FWD_COPYWARP
+#define F3DGS_FWD_COPYWARP 1
+#endif
 #ifndef F3DGS_FWD_A1
 #define F3DGS_FWD_A1 64
 #define F3DGS_FWD_F1 152
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
     const size_t HW = (size_t)H * W;
 
     using L = FwdLayout<BPA>;
-    ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
+    constexpr bool kCopyWarp = CH > 0 && F3DGS_FWD_COPYWARP;  // see producer_loop<>
+    ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0, kCopyWarp ? 2 : 1);
     __syncthreads();
 
     // ======================================================================== producer group
@@ -74,8 +78,10 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
         reg_dec<L::kRegsProducer>();
         if (warp == kProducerWarp) {
             const long long t0 = TICK();
-            producer_loop<CH, false>(ring, args.pa);
+            producer_loop<CH, false, kCopyWarp>(ring, args.pa);
             if (kTiming && args.dbg && (threadIdx.x & 31) == 0) args.dbg[(blockIdx.x * 32 + warp) * 8 + 0] = clock64() - t0;
+        } else if (kCopyWarp && warp == kProducerWarp + 1) {
+            copy_loop<CH>(ring, args.pa);
         }
         return;
     }

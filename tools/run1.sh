@@ -1,7 +1,3 @@
 mkdir -p gpurun_out
-timeout -s KILL 120 python tools/stress_determinism.py c2 60 2>&1 | tail -4
-timeout -s KILL 120 python tools/stress_determinism.py small 200 2>&1 | tail -3
-timeout -s KILL 120 python tools/stress_determinism.py c3_C32 10 2>&1 | tail -3
-timeout -s KILL 120 python tools/stress_determinism.py c1 100 2>&1 | tail -3
-F3DGS_BPA=2 timeout -s KILL 120 python tools/stress_determinism.py c2 40 2>&1 | tail -3
-timeout -s KILL 90 python tools/stage_times.py c3 5 2>&1 | tail -1
+for v in base st5 st8; do echo "== $v"; tools/with_variant.sh $v timeout -s KILL 90 python tools/stage_times.py c3 5 2>&1 | tail -1; done
+timeout -s KILL 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
