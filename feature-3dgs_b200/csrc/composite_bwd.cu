@@ -17,9 +17,30 @@
 //       coalesced 512-byte vector reduction per (block, instance) at C = 128.
 // As in the reference, the feature loss does not feed dL/dalpha (backward.cu:575 is disabled).
 // No features are read at all: the feature gradient needs only w = alpha*T and dL/dout.
+#include <cstdio>
+#include <cstdlib>
+
 #include "composite_common.cuh"
 
 namespace f3dgs {
+
+#ifndef F3DGS_TIMING_BUILD
+#define F3DGS_TIMING_BUILD 0   // build.py sets 1 when env F3DGS_TIMING_BUILD=1: per-role cycle counters (see composite_fwd.cu)
+#endif
+// Diagnostic builds only (WRONG RESULTS, timing experiments): drop the feature-gradient / geometric-gradient global reductions
+// to measure what the red.global.add traffic costs (tools/run_r1e.sh).
+#ifndef F3DGS_DIAG_NO_FEAT_RED
+#define F3DGS_DIAG_NO_FEAT_RED 0
+#endif
+#ifndef F3DGS_DIAG_NO_GEOM_RED
+#define F3DGS_DIAG_NO_GEOM_RED 0
+#endif
+static constexpr bool kTimingB = F3DGS_TIMING_BUILD != 0;
+#define BTICK() ((kTimingB && args.dbg) ? clock64() : 0ll)
+
+#ifndef F3DGS_FFMA2
+#define F3DGS_FFMA2 1   // 1: feature-gradient loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2), see composite_fwd.cu
+#endif
 
 constexpr int kRedSlots = 8;
 constexpr int kRedVals = 10;
@@ -48,6 +69,7 @@ struct BwdArgs {
     float* dL_dfeature;  // [P,C]
     float* dL_dz;        // [P]
     int vec_io;          // bit0: 128-bit loads of dL_dfeat_pix, bit1: red.v4 into dL_dfeature
+    long long* dbg;      // F3DGS_TIMING=1 (timing builds only): per-warp cycle counters [cta][warp][8], else nullptr
 };
 
 template <int CH, int BPA>
@@ -55,7 +77,11 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     RingV2<0>& ring = sm.ring;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The warp index goes through a shuffle so that ptxas knows it is warp-uniform: role branches, ring/slot addresses
+    // and everything loaded from them (instance masks, work ids) then live in uniform registers, the per-quad branches
+    // of the feature loop need no BSSY/BSYNC reconvergence pair, and nothing is re-derived from SR_TID inside the loops.
+    const int warp = F3DGS_UNIFORM_WARP ? __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) : (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
     const size_t HW = (size_t)H * W;
 
@@ -91,8 +117,11 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
         }
         bool do_geom = false;
         const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+        long long tA_full = 0, tA_wempty = 0, tA_flush = 0, nA_hits = 0, nA_pm = 0;
+        const long long tA_total = BTICK();
 
         auto flush = [&]() {
+            const long long tf_ = BTICK();
             __syncwarp();
             for (int r = lane; r < kRedRows; r += 32) {
                 const int slot = r % kRedSlots, v = r / kRedSlots;
@@ -120,15 +149,17 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                         case 6: dst = args.dL_dz + gid; break;
                         default: dst = args.dL_dcolor + 3 * (size_t)gid + (v - 7); break;
                     }
-                    red_add_f1(dst, sum);
+                    if (!F3DGS_DIAG_NO_GEOM_RED) red_add_f1(dst, sum);
+                    else if (sum == 123456.789f) red_add_f1(dst, sum);  // keeps the row sums alive
                 }
             }
             __syncwarp();
             nslots = 0;
+            tA_flush += BTICK() - tf_;
         };
 
         for (;;) {
-            mbar_wait(&ring.full[s], parity);
+            { const long long t_ = BTICK(); mbar_wait(&ring.full[s], parity); tA_full += BTICK() - t_; }
             Stage<0>& st = ring.stage[s];
             const uint32_t n = st.n, last = st.last, first = st.first;
             const int work = st.work;
@@ -170,7 +201,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                 const int b = BPA * a + bi;
                 Px& p = P[bi];
                 WSlot* ws = &ring.ws[b][j];
-                if (CH > 0) mbar_wait(&ring.wempty[b][j], wparity);
+                if (CH > 0) { const long long t_ = BTICK(); mbar_wait(&ring.wempty[b][j], wparity); tA_wempty += BTICK() - t_; }
                 uint32_t km = 0;
                 if (n > 0 && p.wmax > 0) {
                     bool hit = false;
@@ -180,6 +211,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                               (r0.y + r0.w >= p.fby0) && (r0.y - r0.w <= p.fby0 + 3.f);
                     }
                     uint32_t am = __ballot_sync(0xffffffffu, hit);
+                    if (kTimingB) nA_hits += __popc(am);
                     while (am) {
                         // branch-free evaluation of two instances per trip (see composite_fwd.cu)
                         int kk[2];
@@ -249,6 +281,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                             }
                             const uint32_t pm = __ballot_sync(0xffffffffu, contrib);
                             if (pm) {
+                                if (kTimingB) nA_pm++;
                                 if (CH > 0) {
                                     ws->w[k][lane] = wgt;
                                     if (lane == 0) ws->pm[k] = pm;
@@ -282,6 +315,10 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
             if (++s == kStages) { s = 0; parity ^= 1; }
             if (CH > 0 && ++j == kWSlots) { j = 0; wparity ^= 1; }
         }
+        if (kTimingB && args.dbg && lane == 0) {
+            long long* d = args.dbg + (blockIdx.x * 32 + warp) * 8;
+            d[0] = clock64() - tA_total; d[1] = tA_full; d[2] = tA_wempty; d[3] = tA_flush; d[4] = nA_hits; d[5] = nA_pm;
+        }
         if (CH > 0) {
 #pragma unroll
             for (int bi = 0; bi < BPA; bi++) {
@@ -306,15 +343,27 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
         constexpr int NQ = 8 / G;
         const int b = warp - L::kFeatWarp0;
         const int grp = lane / LPR, cl = lane % LPR;
-        float dO[NQ][4][4];  // upstream feature gradient: [quad][pixel in quad][channel]
+        // upstream feature gradient: [quad][pixel in quad][channel]; with F3DGS_FFMA2 the two pixels of a quad row share a
+        // 64-bit register pair (they arrive adjacent from the 128-bit loads, as do their weights from the LDS.128), so one
+        // FFMA2 (weight pair x dO pair + g pair) replaces two FFMAs; g.x / g.y collect the even / odd pixel columns
+#if F3DGS_FFMA2
+        float2 dO2[NQ][2][4];
+#define DO(q, i, c) (((i) & 1) ? dO2[q][(i) >> 1][c].y : dO2[q][(i) >> 1][c].x)
+#else
+        float dO[NQ][4][4];
+#define DO(q, i, c) dO[q][i][c]
+#endif
         int s = 0, j = 0, ch0 = 0;
         uint32_t parity = 0, wparity = 0;
+        long long tF_wfull = 0, tF_full = 0, tF_load = 0, tF_loop = 0, nF_k = 0;
+        const long long tF_total = BTICK();
         for (;;) {
-            mbar_wait(&ring.wfull[b][j], wparity);
+            { const long long t_ = BTICK(); mbar_wait(&ring.wfull[b][j], wparity); tF_wfull += BTICK() - t_; }
             const WSlot& ws = ring.ws[b][j];
             const int work = ws.work;
             if (work < 0) break;
             uint32_t km = ws.km;
+            const long long tL_ = BTICK();
             if (ws.first) {
                 const int tile = work / args.pa.chunks, chunk = work - tile * args.pa.chunks;
                 const int tile_x = tile % args.pa.tiles_x, tile_y = tile / args.pa.tiles_x;
@@ -325,7 +374,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) dO[q][i][c] = 0.f;
+                        for (int c = 0; c < 4; c++) DO(q, i, c) = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int ch = ch0 + c;
@@ -342,10 +391,10 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                                 if (xx >= W) continue;
                                 const int qa = (y >> 1) * 4 + half * 2, i0 = (y & 1) * 2;
                                 const float4 v = ld_nc_f4(plane + (size_t)yy * W + xx);
-                                dO[qa % NQ][i0][c] = v.x;
-                                dO[qa % NQ][i0 + 1][c] = v.y;
-                                dO[(qa + 1) % NQ][i0][c] = v.z;
-                                dO[(qa + 1) % NQ][i0 + 1][c] = v.w;
+                                DO(qa % NQ, i0, c) = v.x;
+                                DO(qa % NQ, i0 + 1, c) = v.y;
+                                DO((qa + 1) % NQ, i0, c) = v.z;
+                                DO((qa + 1) % NQ, i0 + 1, c) = v.w;
                             }
                         }
                     } else {
@@ -355,14 +404,17 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
                                 const int xx = bx0 + (q & 3) * 2 + (i & 1), yy = by0 + (q >> 2) * 2 + (i >> 1);
-                                if (xx < W && yy < H) dO[qi][i][c] = __ldg(plane + (size_t)yy * W + xx);
+                                if (xx < W && yy < H) DO(qi, i, c) = __ldg(plane + (size_t)yy * W + xx);
                             }
                         }
                     }
                 }
             }
-            mbar_wait(&ring.full[s], parity);
+            tF_load += BTICK() - tL_;
+            { const long long t_ = BTICK(); mbar_wait(&ring.full[s], parity); tF_full += BTICK() - t_; }
+            if (kTimingB) nF_k += __popc(km);
             const Stage<0>& st = ring.stage[s];
+            const long long tK_ = BTICK();
             while (km) {
                 const int k = __ffs(km) - 1;
                 km &= km - 1;
@@ -374,6 +426,24 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                     for (int qi = 0; qi < NQ; qi++)
                         w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * (qi * G + grp)]);
                 }
+#if F3DGS_FFMA2
+                float2 gp[4];  // per channel: (sum over even pixel columns, sum over odd pixel columns)
+#pragma unroll
+                for (int c = 0; c < 4; c++) gp[c] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) {
+                    const int q = qi * G + grp;
+                    if ((pm >> (4 * q)) & 0xFu) {
+                        if (!L::kPrefetchW) w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * q]);
+                        const float2 w01 = make_float2(w4[qi].x, w4[qi].y), w23 = make_float2(w4[qi].z, w4[qi].w);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) gp[c] = __ffma2_rn(w01, dO2[qi][0][c], gp[c]);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) gp[c] = __ffma2_rn(w23, dO2[qi][1][c], gp[c]);
+                    }
+                }
+                float g0 = gp[0].x + gp[0].y, g1 = gp[1].x + gp[1].y, g2 = gp[2].x + gp[2].y, g3 = gp[3].x + gp[3].y;
+#else
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
                 for (int qi = 0; qi < NQ; qi++) {
@@ -390,6 +460,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                         }
                     }
                 }
+#endif
 #pragma unroll
                 for (int o = LPR; o < 32; o <<= 1) {
                     g0 += __shfl_xor_sync(0xffffffffu, g0, o);
@@ -399,7 +470,9 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                 }
                 if (grp == 0 && ch0 < C) {
                     float* dst = args.dL_dfeature + (size_t)gid * C + ch0;
-                    if (args.vec_io & 2) {
+                    if (F3DGS_DIAG_NO_FEAT_RED) {
+                        if (g0 + g1 + g2 + g3 == 123456.789f) red_add_f1(dst, g0);  // keeps the FMAs alive
+                    } else if (args.vec_io & 2) {
                         red_add_f4(dst, make_float4(g0, g1, g2, g3));
                     } else {
                         red_add_f1(dst, g0);
@@ -410,12 +483,17 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                 }
             }
             __syncwarp();
+            tF_loop += BTICK() - tK_;
             if (lane == 0) {
                 mbar_arrive(&ring.wempty[b][j]);
                 mbar_arrive(&ring.empty[s]);
             }
             if (++s == kStages) { s = 0; parity ^= 1; }
             if (++j == kWSlots) { j = 0; wparity ^= 1; }
+        }
+        if (kTimingB && args.dbg && lane == 0) {
+            long long* d = args.dbg + (blockIdx.x * 32 + warp) * 8;
+            d[0] = clock64() - tF_total; d[1] = tF_wfull; d[2] = tF_full; d[3] = tF_load; d[4] = nF_k; d[5] = tF_loop;
         }
     }
 }
@@ -443,8 +521,27 @@ static cudaError_t launch_bwd_t(const ViewParams& vp, BwdArgs a, cudaStream_t s)
     cudaError_t e = cudaMemsetAsync(a.pa.work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms > 0 ? num_sms : 148);
+    static long long* dbg = nullptr;
+    const bool timing = kTimingB && getenv("F3DGS_TIMING") != nullptr;  // debug aid: per-role cycle breakdown on stderr
+    if (timing && !dbg) cudaMalloc(&dbg, 256 * 32 * 8 * sizeof(long long));
+    a.dbg = timing ? dbg : nullptr;
+    if (timing) cudaMemsetAsync(dbg, 0, 256 * 32 * 8 * sizeof(long long), s);
     composite_bwd_kernel<CH, BPA><<<grid, Layout<BPA>::kThreads, smem, s>>>(a);
     g_launches++;
+    if (timing) {
+        static long long host[256 * 32 * 8];
+        cudaMemcpyAsync(host, dbg, sizeof(host), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        const int nA = Layout<BPA>::kAlphaWarps, f0 = Layout<BPA>::kFeatWarp0;
+        double A[6] = {0, 0, 0, 0, 0, 0}, F[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < grid; c++) {
+            for (int w = 0; w < nA; w++) for (int i = 0; i < 6; i++) A[i] += host[(c * 32 + kAlphaWarp0 + w) * 8 + i];
+            for (int w = 0; w < 8; w++) for (int i = 0; i < 6; i++) F[i] += host[(c * 32 + f0 + w) * 8 + i];
+        }
+        fprintf(stderr, "[f3dgs timing bwd CH=%d BPA=%d] per-warp mean cycles: alpha total %.0f wait_full %.0f wait_wempty %.0f flush %.0f hits %.0f pm %.0f | feature total %.0f wait_wfull %.0f wait_full %.0f tile_load %.0f k %.0f k_loop %.0f\n",
+                CH, BPA, A[0] / (grid * nA), A[1] / (grid * nA), A[2] / (grid * nA), A[3] / (grid * nA), A[4] / (grid * nA),
+                A[5] / (grid * nA), F[0] / (grid * 8), F[1] / (grid * 8), F[2] / (grid * 8), F[3] / (grid * 8), F[4] / (grid * 8), F[5] / (grid * 8));
+    }
     return cudaGetLastError();
 }
 
@@ -465,7 +562,7 @@ cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, cons
     a.pa.use_bulk = 0;
     a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib; a.dL_dpix = dL_dpix; a.dL_dfeat_pix = dL_dfeat_pix;
     a.dL_ddepth = dL_ddepth; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
-    a.dL_dcolor = dL_dcolor; a.dL_dfeature = dL_dfeature; a.dL_dz = dL_dz; a.vec_io = 0;
+    a.dL_dcolor = dL_dcolor; a.dL_dfeature = dL_dfeature; a.dL_dz = dL_dz; a.vec_io = 0; a.dbg = nullptr;
     if (vp.C == 0) return F3DGS_BWD_DISPATCH(0);
     if (vp.C <= 32) return F3DGS_BWD_DISPATCH(32);
     if (vp.C <= 64) return F3DGS_BWD_DISPATCH(64);

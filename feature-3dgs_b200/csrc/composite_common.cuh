@@ -54,6 +54,9 @@ constexpr int kStageEntries = 32;
 #ifndef F3DGS_WSLOTS
 #define F3DGS_WSLOTS 2
 #endif
+#ifndef F3DGS_UNIFORM_WARP
+#define F3DGS_UNIFORM_WARP 1
+#endif
 constexpr int kStages = F3DGS_STAGES;
 constexpr int kWSlots = F3DGS_WSLOTS;
 constexpr int kDoneSlots = 8;       // > kStages: the producer is never further ahead than that.  Slots are indexed by the

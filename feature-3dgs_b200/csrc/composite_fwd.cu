@@ -34,6 +34,12 @@ namespace f3dgs {
 #define F3DGS_FWD_A1 64
 #define F3DGS_FWD_F1 152
 #endif
+#ifndef F3DGS_FFMA2
+#define F3DGS_FFMA2 1          // 1: feature loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2): half the FMA issue slots
+#endif
+#ifndef F3DGS_FEAT_PREFETCH
+#define F3DGS_FEAT_PREFETCH 0  // 1: software-pipeline the sparse feature loop by one instance (mask + feature float4)
+#endif
 static constexpr bool kTiming = F3DGS_TIMING_BUILD != 0;
 #define TICK() ((kTiming && args.dbg) ? clock64() : 0ll)
 
@@ -64,7 +70,11 @@ template <int CH, int BPA>
 __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel(const FwdArgs args) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RingV2<CH>& ring = *reinterpret_cast<RingV2<CH>*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The warp index goes through a shuffle so that ptxas knows it is warp-uniform: role branches, ring/slot addresses
+    // and everything loaded from them (instance masks, work ids) then live in uniform registers, the per-quad branches
+    // of the feature loop need no BSSY/BSYNC reconvergence pair, and nothing is re-derived from SR_TID inside the loops.
+    const int warp = F3DGS_UNIFORM_WARP ? __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) : (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
     const size_t HW = (size_t)H * W;
 
@@ -375,13 +385,45 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
         constexpr int NQ = 8 / G;                  // 2x2 quads per lane
         const int b = warp - L::kFeatWarp0;
         const int grp = lane / LPR, cl = lane % LPR;
-        float acc[NQ][4][4];  // [quad][pixel in quad][channel]
+        // Accumulators [quad][pixel in quad][channel].  With F3DGS_FFMA2 the two pixels of a quad row share a 64-bit
+        // register pair, so one FFMA2 (feature channel broadcast x weight pair + accumulator pair) does the work of two
+        // FFMAs; each half of an f32x2 FMA is an IEEE fma.rn, so the results are bit-identical to the scalar loop.
+#if F3DGS_FFMA2
+        float2 acc2[NQ][2][4];  // [quad][pixel pair (row of the 2x2 quad)][channel]
+#define ACC(q, i, c) (((i) & 1) ? acc2[q][(i) >> 1][c].y : acc2[q][(i) >> 1][c].x)
+#else
+        float acc[NQ][4][4];
+#define ACC(q, i, c) acc[q][i][c]
+#endif
 #pragma unroll
         for (int q = 0; q < NQ; q++)
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[q][i][c] = 0.f;
+                for (int c = 0; c < 4; c++) ACC(q, i, c) = 0.f;
+#if F3DGS_FFMA2
+#define FEAT_QUAD_FMA(Q, W4)                                                                         \
+    do {                                                                                             \
+        const float2 w01_ = make_float2((W4).x, (W4).y), w23_ = make_float2((W4).z, (W4).w);         \
+        const float fc_[4] = {f.x, f.y, f.z, f.w};                                                   \
+        _Pragma("unroll") for (int c_ = 0; c_ < 4; c_++) {                                           \
+            const float2 fb_ = make_float2(fc_[c_], fc_[c_]);                                        \
+            acc2[Q][0][c_] = __ffma2_rn(fb_, w01_, acc2[Q][0][c_]);                                  \
+            acc2[Q][1][c_] = __ffma2_rn(fb_, w23_, acc2[Q][1][c_]);                                  \
+        }                                                                                            \
+    } while (0)
+#else
+#define FEAT_QUAD_FMA(Q, W4)                                                                         \
+    do {                                                                                             \
+        const float wv_[4] = {(W4).x, (W4).y, (W4).z, (W4).w};                                       \
+        _Pragma("unroll") for (int i_ = 0; i_ < 4; i_++) {                                           \
+            acc[Q][i_][0] = fmaf(f.x, wv_[i_], acc[Q][i_][0]);                                       \
+            acc[Q][i_][1] = fmaf(f.y, wv_[i_], acc[Q][i_][1]);                                       \
+            acc[Q][i_][2] = fmaf(f.z, wv_[i_], acc[Q][i_][2]);                                       \
+            acc[Q][i_][3] = fmaf(f.w, wv_[i_], acc[Q][i_][3]);                                       \
+        }                                                                                            \
+    } while (0)
+#endif
         int s = 0, j = 0;
         uint32_t parity = 0, wparity = 0;
         long long tF_wfull = 0, tF_full = 0, tF_epi = 0, tF_total = TICK(), nF_k = 0;
@@ -410,35 +452,37 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                     asm volatile("" ::: "memory");
 #pragma unroll
                     for (int qi = 0; qi < NQ; qi++) {
-                        const float wv[4] = {w4[qi].x, w4[qi].y, w4[qi].z, w4[qi].w};
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            acc[qi][i][0] = fmaf(f.x, wv[i], acc[qi][i][0]);
-                            acc[qi][i][1] = fmaf(f.y, wv[i], acc[qi][i][1]);
-                            acc[qi][i][2] = fmaf(f.z, wv[i], acc[qi][i][2]);
-                            acc[qi][i][3] = fmaf(f.w, wv[i], acc[qi][i][3]);
-                        }
+                        FEAT_QUAD_FMA(qi, w4[qi]);
                     }
                 }
             } else {
+#if F3DGS_FEAT_PREFETCH
+                // the next instance's pixel mask and feature float4 are requested before this instance's FMAs, so their
+                // LDS latency hides behind the FMA stream instead of heading every instance
+                int kn = km ? __ffs(km) - 1 : 0;
+                uint32_t pm_n = ws.pm[kn];
+                float4 f_n = *reinterpret_cast<const float4*>(&st.feat[kn][cl * 4]);
+                while (km) {
+                    const int k = kn;
+                    const uint32_t pm = pm_n;
+                    const float4 f = f_n;
+                    km &= km - 1;
+                    kn = km ? __ffs(km) - 1 : k;
+                    pm_n = ws.pm[kn];
+                    f_n = *reinterpret_cast<const float4*>(&st.feat[kn][cl * 4]);
+#else
                 while (km) {
                     const int k = __ffs(km) - 1;
                     km &= km - 1;
                     const uint32_t pm = ws.pm[k];
                     const float4 f = *reinterpret_cast<const float4*>(&st.feat[k][cl * 4]);
+#endif
 #pragma unroll
                     for (int qi = 0; qi < NQ; qi++) {
                         const int q = qi * G + grp;
                         if ((pm >> (4 * q)) & 0xFu) {
                             const float4 w4 = *reinterpret_cast<const float4*>(&ws.w[k][4 * q]);
-                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                acc[qi][i][0] = fmaf(f.x, wv[i], acc[qi][i][0]);
-                                acc[qi][i][1] = fmaf(f.y, wv[i], acc[qi][i][1]);
-                                acc[qi][i][2] = fmaf(f.z, wv[i], acc[qi][i][2]);
-                                acc[qi][i][3] = fmaf(f.w, wv[i], acc[qi][i][3]);
-                            }
+                            FEAT_QUAD_FMA(qi, w4);
                         }
                     }
                 }
@@ -467,10 +511,10 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                                 if (yy >= H) continue;
                                 const int qa = (y >> 1) * 4, i0 = (y & 1) * 2;
                                 st_na_f8(plane + (size_t)yy * W + bx0,
-                                         make_float4(acc[qa % NQ][i0][c], acc[qa % NQ][i0 + 1][c],
-                                                     acc[(qa + 1) % NQ][i0][c], acc[(qa + 1) % NQ][i0 + 1][c]),
-                                         make_float4(acc[(qa + 2) % NQ][i0][c], acc[(qa + 2) % NQ][i0 + 1][c],
-                                                     acc[(qa + 3) % NQ][i0][c], acc[(qa + 3) % NQ][i0 + 1][c]));
+                                         make_float4(ACC(qa % NQ, i0, c), ACC(qa % NQ, i0 + 1, c),
+                                                     ACC((qa + 1) % NQ, i0, c), ACC((qa + 1) % NQ, i0 + 1, c)),
+                                         make_float4(ACC((qa + 2) % NQ, i0, c), ACC((qa + 2) % NQ, i0 + 1, c),
+                                                     ACC((qa + 3) % NQ, i0, c), ACC((qa + 3) % NQ, i0 + 1, c)));
                             }
                         } else if (G == 1 && (args.vec_store & 1)) {
                             // rows of 8 pixels -> two 128-bit stores per row
@@ -484,8 +528,8 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                                     if (xx >= W) continue;
                                     const int qa = (y >> 1) * 4 + half * 2, i0 = (y & 1) * 2;
                                     const float4 v =
-                                        make_float4(acc[qa % NQ][i0][c], acc[qa % NQ][i0 + 1][c],
-                                                    acc[(qa + 1) % NQ][i0][c], acc[(qa + 1) % NQ][i0 + 1][c]);
+                                        make_float4(ACC(qa % NQ, i0, c), ACC(qa % NQ, i0 + 1, c),
+                                                    ACC((qa + 1) % NQ, i0, c), ACC((qa + 1) % NQ, i0 + 1, c));
                                     st_na_f4(plane + (size_t)yy * W + xx, v);
                                 }
                             }
@@ -496,7 +540,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
 #pragma unroll
                                 for (int i = 0; i < 4; i++) {
                                     const int xx = bx0 + (q & 3) * 2 + (i & 1), yy = by0 + (q >> 2) * 2 + (i >> 1);
-                                    if (xx < W && yy < H) plane[(size_t)yy * W + xx] = acc[qi][i][c];
+                                    if (xx < W && yy < H) plane[(size_t)yy * W + xx] = ACC(qi, i, c);
                                 }
                             }
                         }
@@ -507,7 +551,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) acc[q][i][c] = 0.f;
+                        for (int c = 0; c < 4; c++) ACC(q, i, c) = 0.f;
             }
             tF_epi += TICK() - tE_;
             if (++s == kStages) { s = 0; parity ^= 1; }
