@@ -38,6 +38,9 @@ namespace f3dgs {
 static constexpr bool kTimingB = F3DGS_TIMING_BUILD != 0;
 #define BTICK() ((kTimingB && args.dbg) ? clock64() : 0ll)
 
+#ifndef F3DGS_PAIR_SKIP
+#define F3DGS_PAIR_SKIP 0   // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
+#endif
 #ifndef F3DGS_FFMA2
 #define F3DGS_FFMA2 1   // 1: feature-gradient loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2), see composite_fwd.cu
 #endif
@@ -206,9 +209,14 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                 if (n > 0 && p.wmax > 0) {
                     bool hit = false;
                     if (lane < n) {
+#if F3DGS_EXACT_CULL
+                        hit = (st.listpos[lane] <= p.wmax) &&
+                              footprint_hits_rect(st.rec0[lane], st.rec1[lane], p.fbx0, p.fbx0 + 7.f, p.fby0, p.fby0 + 3.f);
+#else
                         const float4 r0 = st.rec0[lane];
                         hit = (st.listpos[lane] <= p.wmax) && (r0.x + r0.z >= p.fbx0) && (r0.x - r0.z <= p.fbx0 + 7.f) &&
                               (r0.y + r0.w >= p.fby0) && (r0.y - r0.w <= p.fby0 + 3.f);
+#endif
                     }
                     uint32_t am = __ballot_sync(0xffffffffu, hit);
                     if (kTimingB) nA_hits += __popc(am);
@@ -436,10 +444,20 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                     if ((pm >> (4 * q)) & 0xFu) {
                         if (!L::kPrefetchW) w4[qi] = *reinterpret_cast<const float4*>(&ws.w[k][4 * q]);
                         const float2 w01 = make_float2(w4[qi].x, w4[qi].y), w23 = make_float2(w4[qi].z, w4[qi].w);
+#if F3DGS_PAIR_SKIP
+                        if ((pm >> (4 * q)) & 0x3u)
+#endif
+                        {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) gp[c] = __ffma2_rn(w01, dO2[qi][0][c], gp[c]);
+                            for (int c = 0; c < 4; c++) gp[c] = __ffma2_rn(w01, dO2[qi][0][c], gp[c]);
+                        }
+#if F3DGS_PAIR_SKIP
+                        if ((pm >> (4 * q)) & 0xCu)
+#endif
+                        {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) gp[c] = __ffma2_rn(w23, dO2[qi][1][c], gp[c]);
+                            for (int c = 0; c < 4; c++) gp[c] = __ffma2_rn(w23, dO2[qi][1][c], gp[c]);
+                        }
                     }
                 }
                 float g0 = gp[0].x + gp[0].y, g1 = gp[1].x + gp[1].y, g2 = gp[2].x + gp[2].y, g3 = gp[3].x + gp[3].y;

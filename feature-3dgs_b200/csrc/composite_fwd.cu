@@ -37,6 +37,9 @@ namespace f3dgs {
 #ifndef F3DGS_FFMA2
 #define F3DGS_FFMA2 1          // 1: feature loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2): half the FMA issue slots
 #endif
+#ifndef F3DGS_PAIR_SKIP
+#define F3DGS_PAIR_SKIP 0      // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
+#endif
 #ifndef F3DGS_FEAT_PREFETCH
 #define F3DGS_FEAT_PREFETCH 0  // 1: software-pipeline the sparse feature loop by one instance (mask + feature float4)
 #endif
@@ -263,9 +266,14 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                 if (!blk_done[bi] && n > 0) {
                     bool hit = false;
                     if (lane < n) {
+#if F3DGS_EXACT_CULL
+                        hit = footprint_hits_rect(st.rec0[lane], st.rec1[lane], fbx0[bi], fbx0[bi] + 7.f, fby0[bi],
+                                                  fby0[bi] + 3.f);
+#else
                         const float4 r0 = st.rec0[lane];
                         hit = (r0.x + r0.z >= fbx0[bi]) && (r0.x - r0.z <= fbx0[bi] + 7.f) &&
                               (r0.y + r0.w >= fby0[bi]) && (r0.y - r0.w <= fby0[bi] + 3.f);
+#endif
                     }
                     uint32_t am = __ballot_sync(0xffffffffu, hit);
                     nA_hits += __popc(am);
@@ -401,6 +409,13 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) ACC(q, i, c) = 0.f;
+#define FEAT_ROW_FMA(Q, ROW, W2)                                                                     \
+    do {                                                                                             \
+        const float2 w2_ = (W2);                                                                     \
+        const float fr_[4] = {f.x, f.y, f.z, f.w};                                                   \
+        _Pragma("unroll") for (int c_ = 0; c_ < 4; c_++)                                             \
+            acc2[Q][ROW][c_] = __ffma2_rn(make_float2(fr_[c_], fr_[c_]), w2_, acc2[Q][ROW][c_]);     \
+    } while (0)
 #if F3DGS_FFMA2
 #define FEAT_QUAD_FMA(Q, W4)                                                                         \
     do {                                                                                             \
@@ -482,7 +497,14 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
                         const int q = qi * G + grp;
                         if ((pm >> (4 * q)) & 0xFu) {
                             const float4 w4 = *reinterpret_cast<const float4*>(&ws.w[k][4 * q]);
+#if F3DGS_PAIR_SKIP && F3DGS_FFMA2
+                            // a pixel that did not blend has w = 0 and adds +0: skipping its FMAs leaves every accumulator
+                            // bit-identical (fma(f, +0, acc) == acc for finite f; acc is never -0 because it starts at +0)
+                            if ((pm >> (4 * q)) & 0x3u) FEAT_ROW_FMA(qi, 0, make_float2(w4.x, w4.y));
+                            if ((pm >> (4 * q)) & 0xCu) FEAT_ROW_FMA(qi, 1, make_float2(w4.z, w4.w));
+#else
                             FEAT_QUAD_FMA(qi, w4);
+#endif
                         }
                     }
                 }

@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of round 2 (prepared at the end of round 1, when the GPU budget was spent):
+#   1. every variant library timed and cross-checked in ONE python process (tools/variant_times.py, ~1 s per variant)
+#   2. ncu --set full of the two composite kernels of the default library + raw CSV
+#   3. ncu launch list of the bench command
+# Run tools/prep_r2a.sh on the CPU side first.  Each step has its own timeout and writes into gpurun_out/.
+cd "$(dirname "$0")/.."
+O=gpurun_out; mkdir -p $O
+T0=$(date +%s); el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
+el variants
+timeout -s KILL 400 python tools/variant_times.py c3 5 base u0f0 u1f0 u1f1p ec pr ecpr nofr nogr timing > $O/r2a_variants.jsonl 2> $O/r2a_variants.err
+cat $O/r2a_variants.jsonl | cut -c1-400; grep "f3dgs timing" $O/r2a_variants.err | tail -2
+el "variants, config 2"
+timeout -s KILL 200 python tools/variant_times.py c2 5 base u0f0 ec pr > $O/r2a_variants_c2.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_variants_c2.jsonl | cut -c1-300
+el "ncu full"
+timeout -s KILL 300 ncu --set full --import-source on --clock-control none -k regex:composite -s 2 -c 2 -f -o $O/prof_r2a_c3 python tools/prof_one.py c3 2 > $O/r2a_ncu_full.log 2>&1; tail -2 $O/r2a_ncu_full.log
+timeout -s KILL 120 ncu -i $O/prof_r2a_c3.ncu-rep --page raw --csv > $O/prof_r2a_c3_raw.csv 2>/dev/null
+el "ncu launch list"
+timeout -s KILL 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2a_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/r2a_launches.log 2>&1; tail -1 $O/r2a_launches.log | cut -c1-300
+el done
