@@ -521,24 +521,28 @@ int composite_layout_bpa(int default_bpa);  // composite_fwd.cu
 template <int CH, int BPA>
 static cudaError_t launch_bwd_t(const ViewParams& vp, BwdArgs a, cudaStream_t s) {
     const size_t smem = sizeof(BwdSmem);
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (context): remember it per device ordinal, so that one
+    // process driving several GPUs works too
+    static int sms_of_device[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (sms_of_device[dev] == 0) {
         cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<CH, BPA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms_of_device[dev] = n > 0 ? n : 148;
     }
+    const int num_sms = sms_of_device[dev];
     a.pa.chunks = CH > 0 ? (vp.C + CH - 1) / CH : 1;
     a.vec_io = 0;
     if (vp.W % 4 == 0 && (reinterpret_cast<uintptr_t>(a.dL_dfeat_pix) & 15) == 0) a.vec_io |= 1;
     if (vp.C % 4 == 0 && (reinterpret_cast<uintptr_t>(a.dL_dfeature) & 15) == 0) a.vec_io |= 2;
     cudaError_t e = cudaMemsetAsync(a.pa.work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms > 0 ? num_sms : 148);
+    const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms);
     static long long* dbg = nullptr;
     const bool timing = kTimingB && getenv("F3DGS_TIMING") != nullptr;  // debug aid: per-role cycle breakdown on stderr
     if (timing && !dbg) cudaMalloc(&dbg, 256 * 32 * 8 * sizeof(long long));

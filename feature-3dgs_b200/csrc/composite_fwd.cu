@@ -605,17 +605,21 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
                                 uint32_t* n_contrib, float* out_color, float* out_feature, float* out_depth,
                                 int* work_counter, cudaStream_t s) {
     const size_t smem = sizeof(RingV2<CH>);
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (context): remember it per device ordinal, so that one
+    // process driving several GPUs works too
+    static int sms_of_device[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (sms_of_device[dev] == 0) {
         cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<CH, BPA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms_of_device[dev] = n > 0 ? n : 148;
     }
+    const int num_sms = sms_of_device[dev];
     FwdArgs a;
     a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec;
     a.pa.features = CH > 0 ? features : nullptr;
@@ -632,7 +636,7 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     if (vp.W % 8 == 0 && (reinterpret_cast<uintptr_t>(out_feature) & 31) == 0) a.vec_store |= 2;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms > 0 ? num_sms : 148);
+    const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms);
     static long long* dbg = nullptr;
     const bool timing = getenv("F3DGS_TIMING") != nullptr;  // debug aid: per-role cycle breakdown on stderr
     if (timing && !dbg) cudaMalloc(&dbg, 256 * 32 * 8 * sizeof(long long));
