@@ -51,6 +51,19 @@ constexpr int kRedRows = kRedSlots * kRedVals;
 constexpr int kRedStride = 36;  // floats per row: lanes park at [row][lane] (conflict-free), rows are summed with
                                 // LDS.128 (quarter-warp wavefronts: rows r..r+7 start 4 banks apart -> conflict-free)
 
+// Backward register budget for the 20-warp layout (640 threads x 96 = 61440 registers in the CTA pool):
+// 4x32x40 + 8x32xA + 8x32xF <= 61440  =>  A + F <= 220.  Default 64 / 152; -DF3DGS_BWD_A1=72 -DF3DGS_BWD_F1=144 trades
+// feature-warp headroom for fewer spills in the alpha warps (experiment).
+#ifndef F3DGS_BWD_A1
+#define F3DGS_BWD_A1 64
+#define F3DGS_BWD_F1 152
+#endif
+template <int BPA>
+struct BwdLayout : Layout<BPA> {
+    static constexpr int kRegsAlpha = BPA == 2 ? 104 : F3DGS_BWD_A1;
+    static constexpr int kRegsFeature = BPA == 2 ? 184 : F3DGS_BWD_F1;
+};
+
 struct alignas(128) BwdSmem {
     RingV2<0> ring;
     float red[kBlocksPerTile][kRedRows][kRedStride];
@@ -88,7 +101,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
     const size_t HW = (size_t)H * W;
 
-    using L = Layout<BPA>;
+    using L = BwdLayout<BPA>;
     ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
     __syncthreads();
 
