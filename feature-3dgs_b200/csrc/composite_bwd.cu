@@ -64,10 +64,28 @@ struct BwdLayout : Layout<BPA> {
     static constexpr int kRegsFeature = BPA == 2 ? 184 : F3DGS_BWD_F1;
 };
 
+// F3DGS_BWD_HELPERS=1 (experiment): the row sums + global reductions of the parked geometric terms (`flush`, ~35 of the
+// ~175 instructions an alpha warp spends per blended instance) move to the three otherwise idle warps of the producer
+// group.  Each alpha warp's scratch becomes two buffers of kHelpSlots instances; a full buffer is handed to helper warp
+// (a mod 3) through `rfull`, which sums the rows, issues the red.global.add's and returns the buffer through `rempty`.
+#ifndef F3DGS_BWD_HELPERS
+#define F3DGS_BWD_HELPERS 0
+#endif
+#if F3DGS_BWD_HELPERS
+constexpr int kHelpSlots = kRedSlots / 2;          // instances per hand-off buffer
+constexpr int kHelpRows = kHelpSlots * kRedVals;   // rows per buffer, row = value * kHelpSlots + slot
+constexpr uint32_t kHelpDone = 0xffffffffu;        // red_n sentinel: this alpha warp has finished
+#endif
+
 struct alignas(128) BwdSmem {
     RingV2<0> ring;
     float red[kBlocksPerTile][kRedRows][kRedStride];
     uint32_t red_gid[kBlocksPerTile][kRedSlots];
+#if F3DGS_BWD_HELPERS
+    uint32_t red_n[kBlocksPerTile][2];
+    uint64_t rfull[kBlocksPerTile][2];
+    uint64_t rempty[kBlocksPerTile][2];
+#endif
 };
 
 struct BwdArgs {
@@ -88,6 +106,72 @@ struct BwdArgs {
     long long* dbg;      // F3DGS_TIMING=1 (timing builds only): per-warp cycle counters [cta][warp][8], else nullptr
 };
 
+// destination of reduced value v (0..9) of Gaussian gid: reference backward.cu:560-610 (atomicAdd targets)
+__device__ __forceinline__ float* geom_dst(const BwdArgs& args, int v, uint32_t gid) {
+    switch (v) {
+        case 0: return args.dL_dmean2D + 3 * (size_t)gid;
+        case 1: return args.dL_dmean2D + 3 * (size_t)gid + 1;
+        case 2: return args.dL_dconic + 4 * (size_t)gid;
+        case 3: return args.dL_dconic + 4 * (size_t)gid + 1;
+        case 4: return args.dL_dconic + 4 * (size_t)gid + 3;
+        case 5: return args.dL_dopacity + gid;
+        case 6: return args.dL_dz + gid;
+        default: return args.dL_dcolor + 3 * (size_t)gid + (v - 7);
+    }
+}
+
+#if F3DGS_BWD_HELPERS
+// Helper warp g (0..2) of the producer group: serves the hand-off buffers of alpha warps g, g+3, g+6 round-robin.
+template <int NALPHA>
+__device__ __forceinline__ void helper_loop(BwdSmem& sm, const BwdArgs& args, int g, int lane) {
+    constexpr int kMax = 3;  // alpha warps per helper
+    uint32_t buf[kMax], phase[kMax][2];
+    bool fin[kMax];
+    int active = 0;
+#pragma unroll
+    for (int i = 0; i < kMax; i++) {
+        buf[i] = 0; phase[i][0] = phase[i][1] = 0;
+        fin[i] = (g + 3 * i) >= NALPHA;
+        active += fin[i] ? 0 : 1;
+    }
+    while (active > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int i = 0; i < kMax; i++) {
+            if (fin[i]) continue;
+            const int a = g + 3 * i;
+            const uint32_t b = buf[i];
+            if (!mbar_test(&sm.rfull[a][b], phase[i][b])) continue;
+            progressed = true;
+            phase[i][b] ^= 1;
+            buf[i] = b ^ 1;
+            const uint32_t n = sm.red_n[a][b];
+            if (n == kHelpDone) {
+                fin[i] = true;
+                active--;
+                continue;
+            }
+            for (int r = lane; r < kHelpRows; r += 32) {
+                const int slot = r % kHelpSlots, v = r / kHelpSlots;
+                if (slot < (int)n) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    const float4* row = reinterpret_cast<const float4*>(sm.red[a][b * kHelpRows + r]);
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const float4 q = row[jj];
+                        s0 += q.x; s1 += q.y; s2 += q.z; s3 += q.w;
+                    }
+                    red_add_f1(geom_dst(args, v, sm.red_gid[a][b * kHelpSlots + slot]), (s0 + s1) + (s2 + s3));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.rempty[a][b]);
+        }
+        if (!progressed) __nanosleep(200);
+    }
+}
+#endif
+
 template <int CH, int BPA>
 __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel(const BwdArgs args) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -103,12 +187,25 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
 
     using L = BwdLayout<BPA>;
     ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
+#if F3DGS_BWD_HELPERS
+    if (threadIdx.x == 32) {
+        for (int a = 0; a < kBlocksPerTile; a++)
+            for (int b = 0; b < 2; b++) {
+                mbar_init(&sm.rfull[a][b], 1);
+                mbar_init(&sm.rempty[a][b], 1);
+            }
+        mbar_fence_init();
+    }
+#endif
     __syncthreads();
 
     // ======================================================================== producer group
     if (warp < kAlphaWarp0) {
         reg_dec<L::kRegsProducer>();
         if (warp == kProducerWarp) producer_loop<0, true>(ring, args.pa);
+#if F3DGS_BWD_HELPERS
+        else helper_loop<L::kAlphaWarps>(sm, args, warp - 1, lane);
+#endif
         return;
     }
 
@@ -136,6 +233,22 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
         long long tA_full = 0, tA_wempty = 0, tA_flush = 0, nA_hits = 0, nA_pm = 0;
         const long long tA_total = BTICK();
 
+#if F3DGS_BWD_HELPERS
+        uint32_t rb = 0, ephase = 3u;           // hand-off buffer in use; bit b = parity to wait for on rempty[b] (fresh: 1)
+        bool rb_mine = false;                   // this buffer has been waited for and may be written
+        auto flush = [&]() {                    // hand the current buffer to the helper warp
+            const long long tf_ = BTICK();
+            __syncwarp();
+            if (lane == 0) {
+                sm.red_n[a][rb] = nslots;
+                mbar_arrive(&sm.rfull[a][rb]);
+            }
+            rb ^= 1;
+            nslots = 0;
+            rb_mine = false;
+            tA_flush += BTICK() - tf_;
+        };
+#else
         auto flush = [&]() {
             const long long tf_ = BTICK();
             __syncwarp();
@@ -173,6 +286,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
             nslots = 0;
             tA_flush += BTICK() - tf_;
         };
+#endif
 
         for (;;) {
             { const long long t_ = BTICK(); mbar_wait(&ring.full[s], parity); tA_full += BTICK() - t_; }
@@ -309,11 +423,27 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
                                     km |= 1u << k;
                                 }
                                 if (do_geom) {
+#if F3DGS_BWD_HELPERS
+                                    if (!rb_mine) {  // first instance parked into this buffer: the helper must be done with it
+                                        const long long tf_ = BTICK();
+                                        mbar_wait(&sm.rempty[a][rb], (ephase >> rb) & 1u);
+                                        ephase ^= 1u << rb;
+                                        rb_mine = true;
+                                        tA_flush += BTICK() - tf_;
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < kRedVals; i++)
+                                        red[rb * kHelpRows + i * kHelpSlots + nslots][lane] = v[i];
+                                    if (lane == 0) red_gid[rb * kHelpSlots + nslots] = st.gid[k];
+                                    nslots++;
+                                    if (nslots == kHelpSlots) flush();
+#else
 #pragma unroll
                                     for (int i = 0; i < kRedVals; i++) red[i * kRedSlots + nslots][lane] = v[i];
                                     if (lane == 0) red_gid[nslots] = st.gid[k];
                                     nslots++;
                                     if (nslots == kRedSlots) flush();
+#endif
                                 }
                             }
                         }
@@ -336,6 +466,15 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
             if (++s == kStages) { s = 0; parity ^= 1; }
             if (CH > 0 && ++j == kWSlots) { j = 0; wparity ^= 1; }
         }
+#if F3DGS_BWD_HELPERS
+        // every batch was handed over at the end of its tile; tell the helper that this alpha warp is finished
+        if (!rb_mine) mbar_wait(&sm.rempty[a][rb], (ephase >> rb) & 1u);
+        __syncwarp();
+        if (lane == 0) {
+            sm.red_n[a][rb] = kHelpDone;
+            mbar_arrive(&sm.rfull[a][rb]);
+        }
+#endif
         if (kTimingB && args.dbg && lane == 0) {
             long long* d = args.dbg + (blockIdx.x * 32 + warp) * 8;
             d[0] = clock64() - tA_total; d[1] = tA_full; d[2] = tA_wempty; d[3] = tA_flush; d[4] = nA_hits; d[5] = nA_pm;

@@ -14,4 +14,6 @@ bash tools/build_variants.sh \
   ecpr  "-DF3DGS_EXACT_CULL=1 -DF3DGS_PAIR_SKIP=1" \
   timing "-DF3DGS_TIMING_BUILD=1" \
   nofr  "-DF3DGS_DIAG_NO_FEAT_RED=1" \
-  nogr  "-DF3DGS_DIAG_NO_GEOM_RED=1"
+  nogr  "-DF3DGS_DIAG_NO_GEOM_RED=1" \
+  hp    "-DF3DGS_BWD_HELPERS=1" \
+  hpec  "-DF3DGS_BWD_HELPERS=1 -DF3DGS_EXACT_CULL=1"

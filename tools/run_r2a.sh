@@ -10,6 +10,8 @@ T0=$(date +%s); el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
 el variants
 timeout -s KILL 400 python tools/variant_times.py c3 5 base u0f0 u1f0 u1f1p ec pr ecpr nofr nogr timing > $O/r2a_variants.jsonl 2> $O/r2a_variants.err
 cat $O/r2a_variants.jsonl | cut -c1-400; grep "f3dgs timing" $O/r2a_variants.err | tail -2
+el "risky variants (own process: a hang must not take the sweep down)"
+timeout -s KILL 150 python tools/variant_times.py c3 5 base hp hpec > $O/r2a_variants_hp.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_variants_hp.jsonl | cut -c1-400
 el "variants, config 2"
 timeout -s KILL 200 python tools/variant_times.py c2 5 base u0f0 ec pr > $O/r2a_variants_c2.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_variants_c2.jsonl | cut -c1-300
 el "ncu full"
