@@ -7,6 +7,10 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
 T0=$(date +%s); el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
+# A fresh box pages python/torch/CUDA libraries in from cold storage: the first import can take minutes (round 1 lost four
+# 120-second steps to this).  Pay it once, untimed, before anything with a tight time-out.
+el "warm-up import"
+timeout -s KILL 420 python -c "import torch, numpy; torch.zeros(8, device='cuda').sum().item(); print('torch', torch.__version__, torch.cuda.get_device_name(0))"
 el variants
 timeout -s KILL 400 python tools/variant_times.py c3 5 base u0f0 u1f0 u1f1p ec pr ecpr nofr nogr timing > $O/r2a_variants.jsonl 2> $O/r2a_variants.err
 cat $O/r2a_variants.jsonl | cut -c1-400; grep "f3dgs timing" $O/r2a_variants.err | tail -2
