@@ -32,6 +32,9 @@ namespace f3dgs {
 #ifndef F3DGS_DIAG_NO_FEAT_RED
 #define F3DGS_DIAG_NO_FEAT_RED 0
 #endif
+#ifndef F3DGS_DIAG_NO_FMA
+#define F3DGS_DIAG_NO_FMA 0   // feature warps consume their slots without FMAs or reductions (alpha-limited time)
+#endif
 #ifndef F3DGS_DIAG_NO_GEOM_RED
 #define F3DGS_DIAG_NO_GEOM_RED 0
 #endif
@@ -573,6 +576,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
             tF_load += BTICK() - tL_;
             { const long long t_ = BTICK(); mbar_wait(&ring.full[s], parity); tF_full += BTICK() - t_; }
             if (kTimingB) nF_k += __popc(km);
+            if (F3DGS_DIAG_NO_FMA) km = 0;
             const Stage<0>& st = ring.stage[s];
             const long long tK_ = BTICK();
             while (km) {

@@ -37,6 +37,9 @@ namespace f3dgs {
 #ifndef F3DGS_FFMA2
 #define F3DGS_FFMA2 1          // 1: feature loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2): half the FMA issue slots
 #endif
+#ifndef F3DGS_DIAG_NO_FMA
+#define F3DGS_DIAG_NO_FMA 0    // diagnostic builds only (WRONG RESULTS): feature warps consume their slots without the FMAs
+#endif
 #ifndef F3DGS_PAIR_SKIP
 #define F3DGS_PAIR_SKIP 0      // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
 #endif
@@ -451,6 +454,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
             const uint32_t last = ws.last;
             { const long long t_ = TICK(); mbar_wait(&ring.full[s], parity); tF_full += TICK() - t_; }  // feature rows landed
             nF_k += __popc(km);
+            if (F3DGS_DIAG_NO_FMA) km = 0;
             const Stage<CH>& st = ring.stage[s];
             if (L::kPrefetchW) {
                 // 184-register layout: dense over the block with every operand of an instance fetched before its

@@ -15,5 +15,6 @@ bash tools/build_variants.sh \
   timing "-DF3DGS_TIMING_BUILD=1" \
   nofr  "-DF3DGS_DIAG_NO_FEAT_RED=1" \
   nogr  "-DF3DGS_DIAG_NO_GEOM_RED=1" \
+  nofma "-DF3DGS_DIAG_NO_FMA=1" \
   hp    "-DF3DGS_BWD_HELPERS=1" \
   hpec  "-DF3DGS_BWD_HELPERS=1 -DF3DGS_EXACT_CULL=1"

@@ -12,7 +12,7 @@ T0=$(date +%s); el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
 el "warm-up import"
 timeout -s KILL 420 python -c "import torch, numpy; torch.zeros(8, device='cuda').sum().item(); print('torch', torch.__version__, torch.cuda.get_device_name(0))"
 el variants
-timeout -s KILL 400 python tools/variant_times.py c3 5 base u0f0 u1f0 u1f1p ec pr ecpr nofr nogr timing > $O/r2a_variants.jsonl 2> $O/r2a_variants.err
+timeout -s KILL 400 python tools/variant_times.py c3 5 base u0f0 u1f0 u1f1p ec pr ecpr nofr nogr nofma timing > $O/r2a_variants.jsonl 2> $O/r2a_variants.err
 cat $O/r2a_variants.jsonl | cut -c1-400; grep "f3dgs timing" $O/r2a_variants.err | tail -2
 el "risky variants (own process: a hang must not take the sweep down)"
 timeout -s KILL 150 python tools/variant_times.py c3 5 base hp hpec > $O/r2a_variants_hp.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_variants_hp.jsonl | cut -c1-400
