@@ -9,6 +9,7 @@
 #include <cub/cub.cuh>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -99,15 +100,32 @@ struct ImgLayout {
 };
 struct BinLayout {
     size_t point_list, keys, point_list_unsorted, keys_unsorted, fixed_bytes;
-    explicit BinLayout(size_t R) {
+    size_t list_w = 0, list_meta = 0, list_cnt = 0;  // two-pass mode only (composite_split.cu)
+    explicit BinLayout(size_t R, size_t split_tiles = 0) {
         size_t o = 0;
         point_list = o;           o = align_up(o + R * 4);
         keys = o;                 o = align_up(o + R * 8);
         point_list_unsorted = o;  o = align_up(o + R * 4);
         keys_unsorted = o;        o = align_up(o + R * 8);
+        if (split_tiles) {  // per (tile, 8x4 block) instance lists: 8R entries of capacity (block b of a tile owns `len` of them)
+            list_w = o;     o = align_up(o + 8 * R * 32 * sizeof(float));
+            list_meta = o;  o = align_up(o + 8 * R * sizeof(uint2));
+            list_cnt = o;   o = align_up(o + 8 * split_tiles * sizeof(uint32_t));
+        }
         fixed_bytes = o;
     }
 };
+
+// Two-pass composite (alpha pass + feature pass, composite_split.cu): experimental, opt-in per process with F3DGS_SPLIT=1.
+// The forward and the matching backward must see the same setting (the binning buffer layout depends on it).
+inline bool split_mode(int C) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("F3DGS_SPLIT");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1 && C > 0;
+}
 
 inline int bit_length(uint32_t n) {
     int b = 0;
@@ -271,7 +289,8 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     if (R < 0) return fail(F3DGS_ERR_CUDA, "num_rendered overflowed int32");
 
     // ---- binning buffer
-    const BinLayout bl((size_t)R);
+    const bool split = split_mode(C);
+    const BinLayout bl((size_t)R, split ? tiles : 0);
     const int end_bit = 32 + bit_length((uint32_t)(tiles > 0 ? tiles - 1 : 0));
     size_t sort_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr,
@@ -307,9 +326,20 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     cudaError_t e;
     {
         StageTimer t(F3DGS_STAGE_COMPOSITE_FWD, stream);
-        e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
-                                 out_color, out_feature_map, out_depth, reinterpret_cast<int*>(img + il.counters),
-                                 stream);
+        int* counters = reinterpret_cast<int*>(img + il.counters);
+        if (split) {
+            float* list_w = reinterpret_cast<float*>(bin + bl.list_w);
+            uint2* list_meta = reinterpret_cast<uint2*>(bin + bl.list_meta);
+            uint32_t* list_cnt = reinterpret_cast<uint32_t*>(bin + bl.list_cnt);
+            e = launch_composite_fwd_emit(vp, ranges, point_list, rec, background, final_T, n_contrib, out_color,
+                                          out_depth, list_w, list_meta, list_cnt, counters, stream);
+            if (e == cudaSuccess)
+                e = launch_feature_fwd(vp, ranges, list_w, list_meta, list_cnt, semantic_feature, out_feature_map,
+                                       counters + 32, stream);
+        } else {
+            e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
+                                     out_color, out_feature_map, out_depth, counters, stream);
+        }
     }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_fwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_fwd");
@@ -347,7 +377,8 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
     const size_t tiles = (size_t)vp.grid_x * vp.grid_y;
     const GeomLayout gl((size_t)P);
     const ImgLayout il((size_t)width * height, tiles);
-    const BinLayout bl((size_t)R);
+    const bool split = split_mode(C);
+    const BinLayout bl((size_t)R, split ? tiles : 0);
     const SplatRec* rec = reinterpret_cast<const SplatRec*>(geom_buffer + gl.rec);
     const float* cov3d = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom_buffer + gl.cov3d);
     const uint8_t* clamped = reinterpret_cast<const uint8_t*>(geom_buffer + gl.clamped);
@@ -360,9 +391,24 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
     cudaError_t e;
     {
         StageTimer t(F3DGS_STAGE_COMPOSITE_BWD, stream);
-        e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, dL_dfeaturepix,
-                                 dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dsemantic_feature, dL_dz,
-                                 reinterpret_cast<int*>(image_buffer + il.counters) + 16, stream);
+        int* counters = reinterpret_cast<int*>(image_buffer + il.counters);
+        if (split) {
+            // geometric gradients: the C = 0 backward kernel; feature gradient: one more pass over the forward's lists
+            ViewParams vg = vp;
+            vg.C = 0;
+            e = launch_composite_bwd(vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, nullptr,
+                                     dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, nullptr, dL_dz,
+                                     counters + 16, stream);
+            if (e == cudaSuccess)
+                e = launch_feature_bwd(vp, ranges, reinterpret_cast<const float*>(binning_buffer + bl.list_w),
+                                       reinterpret_cast<const uint2*>(binning_buffer + bl.list_meta),
+                                       reinterpret_cast<const uint32_t*>(binning_buffer + bl.list_cnt), dL_dfeaturepix,
+                                       dL_dsemantic_feature, counters + 48, stream);
+        } else {
+            e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,
+                                     dL_dfeaturepix, dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                     dL_dsemantic_feature, dL_dz, counters + 16, stream);
+        }
     }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_bwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_bwd");

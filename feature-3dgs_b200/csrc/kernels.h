@@ -48,6 +48,20 @@ cudaError_t launch_composite_fwd(const ViewParams& vp, const uint2* ranges, cons
                                  float* final_T, uint32_t* n_contrib, float* out_color,
                                  float* out_feature, float* out_depth, int* work_counter, cudaStream_t s);
 
+// alpha pass of the two-pass mode (composite_split.cu): the C = 0 forward that also writes the per-block instance lists
+cudaError_t launch_composite_fwd_emit(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
+                                      const SplatRec* rec, const float* bg, float* final_T, uint32_t* n_contrib,
+                                      float* out_color, float* out_depth, float* list_w, uint2* list_meta,
+                                      uint32_t* list_cnt, int* work_counter, cudaStream_t s);
+
+// ---- composite_split.cu (two-pass mode, opt-in)
+cudaError_t launch_feature_fwd(const ViewParams& vp, const uint2* ranges, const float* list_w, const uint2* list_meta,
+                               const uint32_t* list_cnt, const float* features, float* out_feature, int* work_counter,
+                               cudaStream_t s);
+cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const float* list_w, const uint2* list_meta,
+                               const uint32_t* list_cnt, const float* dL_dfeat_pix, float* dL_dfeature,
+                               int* work_counter, cudaStream_t s);
+
 // ---- composite_bwd.cu
 cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                  const SplatRec* rec, const float* bg, const float* final_T,

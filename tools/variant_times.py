@@ -3,7 +3,8 @@
     python tools/variant_times.py <config> <iters> base u1f0 timing ...
 
 `base` is feature-3dgs_b200/libf3dgs_b200.so, any other name is feature-3dgs_b200/variants/<name>/libf3dgs_b200.so
-(tools/build_variants.sh).  torch is only the device allocator / stream here; every library is dlopen'ed RTLD_LOCAL and
+(tools/build_variants.sh); `<name>+split` runs the same library in the two-pass mode (F3DGS_SPLIT=1, composite_split.cu) from a
+private copy of the file, so that fused and two-pass results are compared in one process.  torch is only the device allocator / stream here; every library is dlopen'ed RTLD_LOCAL and
 driven through include/f3dgs_b200.h (f3dgs_forward / f3dgs_backward / f3dgs_profile_*), so one import and one scene
 serve all variants (a variant costs ~1 s instead of a fresh python process).  Prints per-stage mean milliseconds and the
 largest difference of every output / gradient against the first variant.  Variants whose name starts with `timing` run
@@ -38,7 +39,14 @@ def ptr(t):
 class Variant:
     def __init__(self, name):
         self.name = name
-        self.lib = ctypes.CDLL(lib_path(name), mode=os.RTLD_LOCAL)
+        path = lib_path(name.split("+")[0])
+        if "+" in name:  # a distinct file = a distinct dlopen handle with its own cached settings
+            import shutil
+            import tempfile
+
+            d = tempfile.mkdtemp(prefix="f3dgs_variant_")
+            path = shutil.copy(path, os.path.join(d, "libf3dgs_b200.so"))
+        self.lib = ctypes.CDLL(path, mode=os.RTLD_LOCAL)
         self.lib.f3dgs_last_error.restype = ctypes.c_char_p
         self.lib.f3dgs_forward.restype = ctypes.c_int
         self.lib.f3dgs_backward.restype = ctypes.c_int
@@ -117,8 +125,11 @@ def main():
     report = {}
     for name in names:
         os.environ.pop("F3DGS_TIMING", None)
+        os.environ.pop("F3DGS_SPLIT", None)
         if name.startswith("timing"):
             os.environ["F3DGS_TIMING"] = "1"
+        if name.endswith("+split"):
+            os.environ["F3DGS_SPLIT"] = "1"  # read once per library instance at its first forward
         v = Variant(name)
         out = dict(color=torch.empty(3, H, W, device=dev), feature=torch.empty(max(C, 1), H, W, device=dev),
                    depth=torch.empty(1, H, W, device=dev), radii=torch.empty(P, dtype=torch.int32, device=dev))
