@@ -118,13 +118,14 @@ struct BinLayout {
 
 // Two-pass composite (alpha pass + feature pass, composite_split.cu): experimental, opt-in per process with F3DGS_SPLIT=1.
 // The forward and the matching backward must see the same setting (the binning buffer layout depends on it).
-inline bool split_mode(int C) {
+// F3DGS_SPLIT=2 additionally runs the two alpha passes with the slim layout (12 warps per CTA, two CTAs per SM).
+inline int split_mode(int C) {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("F3DGS_SPLIT");
-        on = (e && e[0] == '1') ? 1 : 0;
+        on = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
     }
-    return on == 1 && C > 0;
+    return C > 0 ? on : 0;
 }
 
 inline int bit_length(uint32_t n) {
@@ -289,7 +290,7 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     if (R < 0) return fail(F3DGS_ERR_CUDA, "num_rendered overflowed int32");
 
     // ---- binning buffer
-    const bool split = split_mode(C);
+    const int split = split_mode(C);
     const BinLayout bl((size_t)R, split ? tiles : 0);
     const int end_bit = 32 + bit_length((uint32_t)(tiles > 0 ? tiles - 1 : 0));
     size_t sort_bytes = 0;
@@ -331,8 +332,9 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
             float* list_w = reinterpret_cast<float*>(bin + bl.list_w);
             uint2* list_meta = reinterpret_cast<uint2*>(bin + bl.list_meta);
             uint32_t* list_cnt = reinterpret_cast<uint32_t*>(bin + bl.list_cnt);
-            e = launch_composite_fwd_emit(vp, ranges, point_list, rec, background, final_T, n_contrib, out_color,
-                                          out_depth, list_w, list_meta, list_cnt, counters, stream);
+            e = (split == 2 ? launch_composite_fwd_emit_slim : launch_composite_fwd_emit)(
+                vp, ranges, point_list, rec, background, final_T, n_contrib, out_color, out_depth, list_w, list_meta,
+                list_cnt, counters, stream);
             if (e == cudaSuccess)
                 e = launch_feature_fwd(vp, ranges, list_w, list_meta, list_cnt, semantic_feature, out_feature_map,
                                        counters + 32, stream);
@@ -377,7 +379,7 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
     const size_t tiles = (size_t)vp.grid_x * vp.grid_y;
     const GeomLayout gl((size_t)P);
     const ImgLayout il((size_t)width * height, tiles);
-    const bool split = split_mode(C);
+    const int split = split_mode(C);
     const BinLayout bl((size_t)R, split ? tiles : 0);
     const SplatRec* rec = reinterpret_cast<const SplatRec*>(geom_buffer + gl.rec);
     const float* cov3d = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom_buffer + gl.cov3d);
@@ -396,9 +398,14 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
             // geometric gradients: the C = 0 backward kernel; feature gradient: one more pass over the forward's lists
             ViewParams vg = vp;
             vg.C = 0;
-            e = launch_composite_bwd(vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, nullptr,
-                                     dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, nullptr, dL_dz,
-                                     counters + 16, stream);
+            if (split == 2)
+                e = launch_composite_bwd_geom_slim(vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,
+                                                   dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dz,
+                                                   counters + 16, stream);
+            else
+                e = launch_composite_bwd(vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, nullptr,
+                                         dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, nullptr, dL_dz,
+                                         counters + 16, stream);
             if (e == cudaSuccess)
                 e = launch_feature_bwd(vp, ranges, reinterpret_cast<const float*>(binning_buffer + bl.list_w),
                                        reinterpret_cast<const uint2*>(binning_buffer + bl.list_meta),

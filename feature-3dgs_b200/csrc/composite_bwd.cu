@@ -80,8 +80,9 @@ constexpr int kHelpRows = kHelpSlots * kRedVals;   // rows per buffer, row = val
 constexpr uint32_t kHelpDone = 0xffffffffu;        // red_n sentinel: this alpha warp has finished
 #endif
 
-struct alignas(128) BwdSmem {
-    RingV2<0> ring;
+template <typename RING>
+struct alignas(128) BwdSmemT {
+    RING ring;
     float red[kBlocksPerTile][kRedRows][kRedStride];
     uint32_t red_gid[kBlocksPerTile][kRedSlots];
 #if F3DGS_BWD_HELPERS
@@ -90,6 +91,7 @@ struct alignas(128) BwdSmem {
     uint64_t rempty[kBlocksPerTile][2];
 #endif
 };
+using BwdSmem = BwdSmemT<RingV2<0>>;
 
 struct BwdArgs {
     ProducerArgs pa;
@@ -125,8 +127,8 @@ __device__ __forceinline__ float* geom_dst(const BwdArgs& args, int v, uint32_t 
 
 #if F3DGS_BWD_HELPERS
 // Helper warp g (0..2) of the producer group: serves the hand-off buffers of alpha warps g, g+3, g+6 round-robin.
-template <int NALPHA>
-__device__ __forceinline__ void helper_loop(BwdSmem& sm, const BwdArgs& args, int g, int lane) {
+template <int NALPHA, typename SMEM>
+__device__ __forceinline__ void helper_loop(SMEM& sm, const BwdArgs& args, int g, int lane) {
     constexpr int kMax = 3;  // alpha warps per helper
     uint32_t buf[kMax], phase[kMax][2];
     bool fin[kMax];
@@ -175,11 +177,17 @@ __device__ __forceinline__ void helper_loop(BwdSmem& sm, const BwdArgs& args, in
 }
 #endif
 
-template <int CH, int BPA>
-__global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel(const BwdArgs args) {
+// SLIM (geometric pass of the two-pass mode, CH == 0): 12 warps, ring without weight slots (106 KB of shared memory instead
+// of 175 KB), two CTAs per SM; the alpha warps keep the launch register count (80) instead of shrinking to 64.
+template <int CH, int BPA, bool SLIM = false>
+__global__ void __launch_bounds__(SLIM ? (kAlphaWarp0 + Layout<BPA>::kAlphaWarps) * 32 : Layout<BPA>::kThreads, SLIM ? 2 : 1)
+composite_bwd_kernel(const BwdArgs args) {
+    static_assert(!SLIM || CH == 0, "the slim layout has no feature warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-    RingV2<0>& ring = sm.ring;
+    using RING = typename RingSelect<0, SLIM>::type;
+    using SMEM = BwdSmemT<RING>;
+    SMEM& sm = *reinterpret_cast<SMEM*>(smem_raw);
+    RING& ring = sm.ring;
     // The warp index goes through a shuffle so that ptxas knows it is warp-uniform: role branches, ring/slot addresses
     // and everything loaded from them (instance masks, work ids) then live in uniform registers, the per-quad branches
     // of the feature loop need no BSSY/BSYNC reconvergence pair, and nothing is re-derived from SR_TID inside the loops.
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
     const size_t HW = (size_t)H * W;
 
     using L = BwdLayout<BPA>;
-    ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
+    ring_init<0>(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
 #if F3DGS_BWD_HELPERS
     if (threadIdx.x == 32) {
         for (int a = 0; a < kBlocksPerTile; a++)
@@ -205,16 +213,16 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_bwd_kernel
     // ======================================================================== producer group
     if (warp < kAlphaWarp0) {
         reg_dec<L::kRegsProducer>();
-        if (warp == kProducerWarp) producer_loop<0, true>(ring, args.pa);
+        if (warp == kProducerWarp) producer_loop<0, true, false, RING>(ring, args.pa);
 #if F3DGS_BWD_HELPERS
-        else helper_loop<L::kAlphaWarps>(sm, args, warp - 1, lane);
+        else helper_loop<L::kAlphaWarps, SMEM>(sm, args, warp - 1, lane);
 #endif
         return;
     }
 
     // ======================================================================== alpha warps
     if (warp < L::kFeatWarp0) {
-        reg_dec<L::kRegsAlpha>();
+        if (!SLIM) reg_dec<L::kRegsAlpha>();
         const int a = warp - kAlphaWarp0;  // owns blocks BPA*a .. BPA*a + BPA-1
         float(*red)[kRedStride] = sm.red[a];
         uint32_t* red_gid = sm.red_gid[a];
@@ -720,6 +728,42 @@ static cudaError_t launch_bwd_t(const ViewParams& vp, BwdArgs a, cudaStream_t s)
                 CH, BPA, A[0] / (grid * nA), A[1] / (grid * nA), A[2] / (grid * nA), A[3] / (grid * nA), A[4] / (grid * nA),
                 A[5] / (grid * nA), F[0] / (grid * 8), F[1] / (grid * 8), F[2] / (grid * 8), F[3] / (grid * 8), F[4] / (grid * 8), F[5] / (grid * 8));
     }
+    return cudaGetLastError();
+}
+
+// Geometric-gradient pass of the two-pass mode with the slim layout (F3DGS_SPLIT=2): C = 0 kernel, two CTAs per SM.
+cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
+                                           const SplatRec* rec, const float* bg, const float* final_T,
+                                           const uint32_t* n_contrib, const float* dL_dpix, const float* dL_ddepth,
+                                           float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                                           float* dL_dz, int* work_counter, cudaStream_t s) {
+    using SMEM = BwdSmemT<RingSlim>;
+    const size_t smem = sizeof(SMEM);
+    static int sms_of_device[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (sms_of_device[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms_of_device[dev] = n > 0 ? n : 148;
+    }
+    BwdArgs a;
+    a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec; a.pa.features = nullptr;
+    a.pa.n_contrib = n_contrib; a.pa.work_counter = work_counter;
+    a.pa.W = vp.W; a.pa.H = vp.H; a.pa.C = 0;
+    a.pa.tiles_x = (int)vp.grid_x; a.pa.num_tiles = (int)(vp.grid_x * vp.grid_y); a.pa.chunks = 1; a.pa.use_bulk = 0;
+    a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib; a.dL_dpix = dL_dpix; a.dL_dfeat_pix = nullptr;
+    a.dL_ddepth = dL_ddepth; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
+    a.dL_dcolor = dL_dcolor; a.dL_dfeature = nullptr; a.dL_dz = dL_dz; a.vec_io = 0; a.dbg = nullptr;
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const int grid = min(a.pa.num_tiles, 2 * sms_of_device[dev]);
+    composite_bwd_kernel<0, 1, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
+    g_launches++;
     return cudaGetLastError();
 }
 

@@ -89,6 +89,7 @@ struct alignas(128) WSlot {
 
 template <int CH>
 struct alignas(128) RingV2 {
+    static constexpr int kWB = kBlocksPerTile, kWJ = kWSlots;  // dimensions of the weight-slot ring
     Stage<CH> stage[kStages];
     WSlot ws[kBlocksPerTile][kWSlots];
     uint64_t full[kStages];
@@ -97,6 +98,21 @@ struct alignas(128) RingV2 {
     uint64_t wfull[kBlocksPerTile][kWSlots];
     uint64_t wempty[kBlocksPerTile][kWSlots];
     uint32_t done_mask[kDoneSlots];  // bit b set: pixel block b of that work item needs no more instances
+};
+
+// The same ring without weight slots, for the kernels that have no feature warps (alpha passes of the two-pass mode):
+// 14 KB instead of 83 KB of shared memory, so that two CTAs fit on an SM.  The one-element `ws` / `wfull` / `wempty` only
+// keep the (never executed, CH == 0) weight-slot code of the kernels well-formed.
+struct alignas(128) RingSlim {
+    static constexpr int kWB = 1, kWJ = 1;
+    Stage<0> stage[kStages];
+    WSlot ws[1][1];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t listed[kStages];
+    uint64_t wfull[1][1];
+    uint64_t wempty[1][1];
+    uint32_t done_mask[kDoneSlots];
 };
 
 #ifndef F3DGS_EXACT_CULL
@@ -140,6 +156,15 @@ __device__ __forceinline__ bool footprint_hits_rect(const float4 r0, const float
 #endif
 }
 
+template <int CH, bool SLIM>
+struct RingSelect {
+    using type = RingV2<CH>;
+};
+template <int CH>
+struct RingSelect<CH, true> {
+    using type = RingSlim;
+};
+
 // pixel <-> lane mapping inside a block: 2x2 quads, quad q = lane>>2 laid out 4 across
 __device__ __forceinline__ int lane_px(int lane) { return ((lane >> 2) & 3) * 2 + (lane & 1); }
 __device__ __forceinline__ int lane_py(int lane) { return (lane >> 4) * 2 + ((lane >> 1) & 1); }
@@ -153,8 +178,8 @@ __device__ __forceinline__ void reg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-template <int CH>
-__device__ __forceinline__ void ring_init(RingV2<CH>& ring, int n_stage_consumers, bool use_w, int n_full_arrivals = 1) {
+template <int CH, typename RING>
+__device__ __forceinline__ void ring_init(RING& ring, int n_stage_consumers, bool use_w, int n_full_arrivals = 1) {
     // called by all threads before the role split; followed by __syncthreads()
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -162,8 +187,8 @@ __device__ __forceinline__ void ring_init(RingV2<CH>& ring, int n_stage_consumer
             mbar_init(&ring.empty[s], n_stage_consumers);
             mbar_init(&ring.listed[s], 1);
         }
-        for (int b = 0; b < kBlocksPerTile; b++)
-            for (int j = 0; j < kWSlots; j++) {
+        for (int b = 0; b < RING::kWB; b++)
+            for (int j = 0; j < RING::kWJ; j++) {
                 mbar_init(&ring.wfull[b][j], 1);
                 mbar_init(&ring.wempty[b][j], 1);
             }
@@ -200,8 +225,8 @@ struct ProducerArgs {
 // copy costs the issuing warp ~9 instructions and an R2UR round trip per row (UBLKCP takes uniform registers, so the
 // compiler serialises the lanes); with 2.4 M rows per view at config 3 that was ~45% of the producer's instructions
 // and the producer was busy 85% of the time, i.e. the pipeline's critical path (ncu source counters, round 1).
-template <int CH, bool REVERSE, bool COPYWARP = false>
-__device__ __forceinline__ void producer_loop(RingV2<CH>& ring, const ProducerArgs& pa) {
+template <int CH, bool REVERSE, bool COPYWARP = false, typename RING = RingV2<CH>>
+__device__ __forceinline__ void producer_loop(RING& ring, const ProducerArgs& pa) {
     const int lane = threadIdx.x & 31;
     int s = 0;
     uint32_t empty_parity = 1;  // fresh barrier: waiting on parity 1 falls through

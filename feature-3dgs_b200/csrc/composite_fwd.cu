@@ -76,10 +76,15 @@ struct FwdLayout : Layout<BPA> {
     static constexpr bool kPrefetchW = BPA == 2 || F3DGS_FWD_F1 >= 168;
 };
 
-template <int CH, int BPA, bool EMIT = false>
-__global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel(const FwdArgs args) {
+// SLIM (two-pass alpha pass only, CH == 0): no feature warps are launched (12 warps), the ring has no weight slots and two
+// CTAs share an SM (launch bound 384 x 2 -> 80 registers; the alpha warps keep them instead of shrinking to 64).
+template <int CH, int BPA, bool EMIT = false, bool SLIM = false>
+__global__ void __launch_bounds__(SLIM ? (kAlphaWarp0 + Layout<BPA>::kAlphaWarps) * 32 : Layout<BPA>::kThreads, SLIM ? 2 : 1)
+composite_fwd_kernel(const FwdArgs args) {
+    static_assert(!SLIM || CH == 0, "the slim layout has no feature warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    RingV2<CH>& ring = *reinterpret_cast<RingV2<CH>*>(smem_raw);
+    using RING = typename RingSelect<CH, SLIM>::type;
+    RING& ring = *reinterpret_cast<RING*>(smem_raw);
     // The warp index goes through a shuffle so that ptxas knows it is warp-uniform: role branches, ring/slot addresses
     // and everything loaded from them (instance masks, work ids) then live in uniform registers, the per-quad branches
     // of the feature loop need no BSSY/BSYNC reconvergence pair, and nothing is re-derived from SR_TID inside the loops.
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
 
     using L = FwdLayout<BPA>;
     constexpr bool kCopyWarp = CH > 0 && F3DGS_FWD_COPYWARP;  // see producer_loop<>
-    ring_init(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0, kCopyWarp ? 2 : 1);
+    ring_init<CH>(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0, kCopyWarp ? 2 : 1);
     __syncthreads();
 
     // ======================================================================== producer group
@@ -98,17 +103,17 @@ __global__ void __launch_bounds__(Layout<BPA>::kThreads, 1) composite_fwd_kernel
         reg_dec<L::kRegsProducer>();
         if (warp == kProducerWarp) {
             const long long t0 = TICK();
-            producer_loop<CH, false, kCopyWarp>(ring, args.pa);
+            producer_loop<CH, false, kCopyWarp, RING>(ring, args.pa);
             if (kTiming && args.dbg && (threadIdx.x & 31) == 0) args.dbg[(blockIdx.x * 32 + warp) * 8 + 0] = clock64() - t0;
         } else if (kCopyWarp && warp == kProducerWarp + 1) {
-            copy_loop<CH>(ring, args.pa);
+            if constexpr (kCopyWarp) copy_loop<CH>(ring, args.pa);
         }
         return;
     }
 
     // ======================================================================== alpha warps
     if (warp < L::kFeatWarp0) {
-        reg_dec<L::kRegsAlpha>();
+        if (!SLIM) reg_dec<L::kRegsAlpha>();
         const int a = warp - kAlphaWarp0;  // owns blocks BPA*a .. BPA*a + BPA-1
         int s = 0, j = 0;
         uint32_t parity = 0, wparity = 1;  // wempty: fresh barrier falls through on parity 1
@@ -724,6 +729,41 @@ cudaError_t launch_composite_fwd_emit(const ViewParams& vp, const uint2* ranges,
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles, sms_of_device[dev]);
     composite_fwd_kernel<0, 1, true><<<grid, Layout<1>::kThreads, smem, s>>>(a);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// Same alpha pass with the slim layout: 12 warps per CTA, two CTAs per SM (F3DGS_SPLIT=2).
+cudaError_t launch_composite_fwd_emit_slim(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
+                                           const SplatRec* rec, const float* bg, float* final_T, uint32_t* n_contrib,
+                                           float* out_color, float* out_depth, float* list_w, uint2* list_meta,
+                                           uint32_t* list_cnt, int* work_counter, cudaStream_t s) {
+    const size_t smem = sizeof(RingSlim);
+    static int sms_of_device[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (sms_of_device[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<0, 1, true, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms_of_device[dev] = n > 0 ? n : 148;
+    }
+    FwdArgs a;
+    a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec;
+    a.pa.features = nullptr; a.pa.n_contrib = nullptr; a.pa.work_counter = work_counter;
+    a.pa.W = vp.W; a.pa.H = vp.H; a.pa.C = 0;
+    a.pa.tiles_x = (int)vp.grid_x; a.pa.num_tiles = (int)(vp.grid_x * vp.grid_y); a.pa.chunks = 1; a.pa.use_bulk = 0;
+    a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib;
+    a.out_color = out_color; a.out_feature = nullptr; a.out_depth = out_depth;
+    a.vec_store = 0; a.dbg = nullptr;
+    a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const int grid = min(a.pa.num_tiles, 2 * sms_of_device[dev]);
+    composite_fwd_kernel<0, 1, true, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
     g_launches++;
     return cudaGetLastError();
 }

@@ -130,6 +130,8 @@ def main():
             os.environ["F3DGS_TIMING"] = "1"
         if name.endswith("+split"):
             os.environ["F3DGS_SPLIT"] = "1"  # read once per library instance at its first forward
+        if name.endswith("+split2"):
+            os.environ["F3DGS_SPLIT"] = "2"
         v = Variant(name)
         out = dict(color=torch.empty(3, H, W, device=dev), feature=torch.empty(max(C, 1), H, W, device=dev),
                    depth=torch.empty(1, H, W, device=dev), radii=torch.empty(P, dtype=torch.int32, device=dev))
