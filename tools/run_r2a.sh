@@ -17,6 +17,7 @@ cat $O/r2a_variants.jsonl | cut -c1-400; grep "f3dgs timing" $O/r2a_variants.err
 el "risky variants (own process: a hang must not take the sweep down)"
 timeout -s KILL 150 python tools/variant_times.py c3 5 base hp hpec > $O/r2a_variants_hp.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_variants_hp.jsonl | cut -c1-400
 el "two-pass mode (own process)"
+F3DGS_SPLIT=1 timeout -s KILL 150 python tools/check_lists.py small 40 2>&1 | tail -2 | tee $O/r2a_lists.txt
 timeout -s KILL 150 python tools/variant_times.py small 3 base base+split base+split2 > $O/r2a_split_small.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_split_small.jsonl | cut -c1-600
 timeout -s KILL 200 python tools/variant_times.py c3 5 base base+split base+split2 > $O/r2a_split_c3.jsonl 2>> $O/r2a_variants.err; cat $O/r2a_split_c3.jsonl | cut -c1-600
 F3DGS_SPLIT=1 timeout -s KILL 400 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "small_configs or feature_widths or image_shapes or c2_vs" 2>&1 | tail -3 | tee $O/r2a_split_pytest.txt
