@@ -144,6 +144,12 @@ def main():
     ap.add_argument("--config", default="c3", choices=list(scenegen.CONFIGS))
     ap.add_argument("--views-per-rank", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-views", type=int, default=64,
+                    help="config c4 only: size of the view batch sharded over the ranks (BASELINE: 64)")
+    ap.add_argument("--l2-flush", action="store_true",
+                    help="write a 512 MB buffer between timed steps (outside the per-step event pairs)")
+    ap.add_argument("--ref-debug", action="store_true",
+                    help="reference arm only: debug=True, the reference scripts' default (arguments/__init__.py:71)")
     args = ap.parse_args()
 
     import torch
@@ -158,15 +164,20 @@ def main():
     have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"ref_rast_C{scenegen.CONFIGS[args.config]['C'] or 1}.so"))
 
     cfgd = scenegen.CONFIGS[args.config]
+    fwd_only = args.config == "c5"          # BASELINE.json configs[4]: forward-only render throughput
+    strong = args.config == "c4"            # BASELINE.json configs[3]: one 64-view batch sharded over the ranks
+    mode = "fwd-only" if fwd_only else "fwd+bwd"
     cfg_str = (f"{args.config}: {cfgd['P']} Gaussians, {cfgd['W']}x{cfgd['H']}, SH deg {cfgd['sh_degree']}, "
-               f"feat_dim {cfgd['C']}, fwd+bwd")
+               f"feat_dim {cfgd['C']}, {mode}")
+    metric = METRIC if args.config == "c3" else (
+        f"views/sec {mode} @{cfgd['P']} Gaussians/{cfgd['W']}x{cfgd['H']}/feat_dim={cfgd['C']}")
 
     if args.impl == "reference" and not have_ref:
         # no reference build on this box: time the CPU port instead (rank 0 only)
         if rank == 0:
             sc = scenegen.make_config(args.config, views=1)
             cb = cpu_baseline(sc, cfg_str)
-            print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "views/s",
+            print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "views/s",
                               "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                               "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True, "scaling": "weak",
                               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -182,6 +193,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     VPR = args.views_per_rank
+    if strong:
+        if args.batch_views % world:
+            raise SystemExit("config c4 shards one view batch: WORLD_SIZE must divide --batch-views")
+        VPR = args.batch_views // world
     n_views = VPR * world
     scene = scenegen.make_config(args.config, views=n_views)
     C, P = scene.C, scene.P
@@ -192,9 +207,17 @@ def main():
         from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
         from diff_gaussian_rasterization.parallel import FlatGradBuffer, shard_views
     else:
+        # The reference arm must not map this repo's native libraries: the host-side helpers (flat gradient buffer, view
+        # sharding -- pure torch) are loaded by FILE PATH so that the package __init__ (which imports _C) never runs.
+        import importlib.util
+
         sys.path.insert(0, ROOT)
         from oracle import ref_wrapper as rw
-        from diff_gaussian_rasterization.parallel import FlatGradBuffer, shard_views  # host-side helper only
+        spec = importlib.util.spec_from_file_location(
+            "f3dgs_parallel_helpers", os.path.join(ROOT, "feature-3dgs_b200", "diff_gaussian_rasterization", "parallel.py"))
+        _par = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_par)
+        FlatGradBuffer, shard_views = _par.FlatGradBuffer, _par.shard_views
         _C = None
 
     t = scenegen.to_torch(scene, dev, requires_grad=True)
@@ -215,7 +238,8 @@ def main():
     def make_rasterizer(cam, packed):
         kw = dict(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
                   viewmatrix=packed[0:16].view(4, 4), projmatrix=packed[16:32].view(4, 4),
-                  sh_degree=scene.sh_degree, campos=packed[32:35], prefiltered=False, debug=False)
+                  sh_degree=scene.sh_degree, campos=packed[32:35], prefiltered=False,
+                  debug=bool(args.ref_debug and args.impl == "reference"))
         if args.impl == "ours":
             return GaussianRasterizer(GaussianRasterizationSettings(**kw))
         return rw.RefRasterizer(kw, C)
@@ -229,6 +253,12 @@ def main():
     stats = {}
 
     def step_device():
+        if fwd_only:
+            with torch.no_grad():
+                for i, cam in enumerate(cams):
+                    color, feat, radii, depth = render(cam, cam_dev[i])
+                    stats["radii"] = radii
+            return
         flat.zero_()
         for i, cam in enumerate(cams):
             color, feat, radii, depth = render(cam, cam_dev[i])
@@ -244,8 +274,15 @@ def main():
     cam_stage = [torch.empty_like(d) for d in cam_dev]
 
     def step_e2e():
-        flat.zero_()
         total = torch.zeros((), device=dev)
+        if fwd_only:
+            with torch.no_grad():
+                for i, cam in enumerate(cams):
+                    cam_stage[i].copy_(cam_host[i], non_blocking=True)
+                    color, feat, radii, depth = render(cam, cam_stage[i])
+                    total = total + (color * gc).sum() + (depth * gd).sum() + ((feat * gf).sum() if C else 0.0)
+            return float(total.item())
+        flat.zero_()
         for i, cam in enumerate(cams):
             cam_stage[i].copy_(cam_host[i], non_blocking=True)  # H2D of this view's camera
             color, feat, radii, depth = render(cam, cam_stage[i])
@@ -262,17 +299,33 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if args.l2_flush else None
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if flush_buf is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            total_ms = e0.elapsed_time(e1)
+        else:
+            # one event pair per step; the L2 flush (a 512 MB fill, 4x the 126 MB L2) sits between the pairs
+            pairs = []
+            for _ in range(steps):
+                flush_buf.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                pairs.append((a, b))
+            barrier()
+            total_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        ms = torch.tensor([total_ms], device=dev)
         if distributed:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
         return float(ms.item())
@@ -310,20 +363,32 @@ def main():
     radii = stats["radii"]
     V = int((radii > 0).sum().item())
     out = {
-        "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": metric, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg_str, "views_per_rank_per_step": VPR, "views_per_step": views_per_step,
                    "parallelism": f"view-sharded dp{world}, 1 grad all-reduce/step" if distributed else "single GPU",
-                   "l2": "inputs exceed L2 (features 512 MB, upstream grads 1.1 GB per view at c3); no explicit flush",
-                   "api": "GaussianRasterizer autograd API (forward + torch.autograd.backward)"},
+                   "l2": ("explicit flush: 512 MB fill between timed steps, outside the per-step event pairs" if args.l2_flush
+                          else "inputs exceed the 126 MB L2 (per view: features P*C*4 B, upstream grads C*H*W*4 B); no explicit flush"),
+                   "api": "GaussianRasterizer autograd API (forward" + ("" if fwd_only else " + torch.autograd.backward") + ")",
+                   "e2e_moves": "per view: 35 floats of camera state from pinned host memory (H2D); per step: the scalar loss "
+                                "(D2H). Gaussian parameters, upstream-gradient weights and rendered maps stay in HBM (model "
+                                "state and loss inputs of a training loop, as in the reference train.py)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
     }
     if args.impl == "reference":
         out["impl"] = "reference"
-        out["config"]["reference_kind"] = "unmodified reference CUDA extension (oracle/_ref, sm_100a build), debug=False"
+        out["config"]["reference_kind"] = ("unmodified reference CUDA kernels + _C binding (oracle/_ref, sm_100a build), debug="
+                                           + str(bool(args.ref_debug)) + "; its 60-line Python autograd shim is restated "
+                                           "in oracle/ref_wrapper.py (the reference tree does not travel to the GPU box)")
+        maps = open("/proc/self/maps").read()
+        mine = sorted({ln.split("/")[-1] for ln in maps.splitlines()
+                       if "libf3dgs_b200" in ln or "diff_gaussian_rasterization/_C" in ln})
+        assert not mine, f"reference arm mapped this repo's native libraries: {mine}"
+        out["config"]["native_libs_of_this_repo_mapped"] = mine
         out["gpu_launches"] = 0
     else:
         out["gpu_launches"] = int(launches)
@@ -337,7 +402,7 @@ def main():
                                          cams[-1].tanfovy, H, W, t["shs"], scene.sh_degree, cam_dev[-1][32:35], False, False)
         R = int(raw[0])
         alg = algorithmic_bytes(V, R, tiles, HW, C)
-        dom = max(("composite_fwd", "composite_bwd"), key=lambda k: per_launch[k] * (1 if C <= 128 else 1))
+        dom = "composite_fwd" if fwd_only else max(("composite_fwd", "composite_bwd"), key=lambda k: per_launch[k])
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

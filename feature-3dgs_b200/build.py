@@ -45,8 +45,26 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _flags_changed():
+    """Objects are only reusable for the flags they were built with (experiment / timing builds change the code)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode()).hexdigest()
+    stamp = os.path.join(OBJ, "flags.sha256")
+    old = open(stamp).read().strip() if os.path.exists(stamp) else None
+    if old != h:
+        with open(stamp, "w") as f:
+            f.write(h)
+        return True
+    return False
+
+
 def build_lib(force=False):
     os.makedirs(OBJ, exist_ok=True)
+    if any("F3DGS_DIAG_" in f for f in NVCC_FLAGS):
+        raise RuntimeError("F3DGS_DIAG_* builds produce wrong results on purpose: build them with tools/build_variants.sh "
+                           "into feature-3dgs_b200/variants/, never as the product library")
+    force = _flags_changed() or force
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HDRS]
     jobs, objs = [], []
     for cu in CU:

@@ -19,7 +19,7 @@
 #include "kernels.h"
 
 namespace f3dgs {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }
 using namespace f3dgs;
 
@@ -174,7 +174,7 @@ extern "C" {
 
 int f3dgs_abi_version(void) { return F3DGS_ABI_VERSION; }
 const char* f3dgs_last_error(void) { return t_error.c_str(); }
-unsigned long long f3dgs_launch_count(void) { return g_launches; }
+unsigned long long f3dgs_launch_count(void) { return g_launches.load(); }
 
 void f3dgs_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_profile_mu);

@@ -674,9 +674,9 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles * a.pa.chunks, num_sms);
     static long long* dbg = nullptr;
-    const bool timing = getenv("F3DGS_TIMING") != nullptr;  // debug aid: per-role cycle breakdown on stderr
+    const bool timing = kTiming && getenv("F3DGS_TIMING") != nullptr;  // debug aid (timing builds only): per-role cycle breakdown on stderr
     if (timing && !dbg) cudaMalloc(&dbg, 256 * 32 * 8 * sizeof(long long));
-    a.dbg = (kTiming && timing) ? dbg : nullptr;
+    a.dbg = timing ? dbg : nullptr;
     if (timing) cudaMemsetAsync(dbg, 0, 256 * 32 * 8 * sizeof(long long), s);
     composite_fwd_kernel<CH, BPA><<<grid, Layout<BPA>::kThreads, smem, s>>>(a);
     g_launches++;

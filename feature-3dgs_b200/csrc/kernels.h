@@ -2,11 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
+
 #include "common.cuh"
 
 namespace f3dgs {
 
-extern unsigned long long g_launches;  // kernels launched by this library (api.cu)
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library (api.cu)
 
 struct ViewParams {
     int P, D, M, C;

@@ -297,16 +297,16 @@ def c3_scene():
     return scenegen.make_config("c3")
 
 
-def test_c3_full_size_vs_reference(c3_scene):
-    """BASELINE.json's metric configuration itself: 1M Gaussians, 1080p, C=128 (device-side comparison)."""
+def _full_size_vs_reference(sc, with_grads, label):
+    """Device-side comparison of one full-size view against the reference build; prints the worst violation ratio
+    (|a-b| / tolerance, <= 1 passes) of every float tensor so the margin is on record in the test log."""
     import torch
     from oracle import ref_wrapper as rw
 
-    sc = c3_scene
     if not rw.available(sc.C):
-        pytest.skip("no reference build for C=128 on this box")
+        pytest.skip(f"no reference build for C={sc.C} on this box")
     cam = sc.cameras[0]
-    grads = scenegen.upstream_grads(cam.image_height, cam.image_width, sc.C)
+    grads = scenegen.upstream_grads(cam.image_height, cam.image_width, sc.C) if with_grads else None
     ours = parity.run_ours(sc, cam, grads=grads)
     ref = parity.run_ref(sc, cam, grads=grads)
     for k in ("radii", "point_list", "ranges", "n_contrib"):
@@ -315,16 +315,37 @@ def test_c3_full_size_vs_reference(c3_scene):
     for k in ("color", "depth", "final_T"):
         assert np.array_equal(ours[k], ref[k]), k
 
-    def viol(a, b):
+    def viol(a, b, atol):
         a, b = torch.from_numpy(a).cuda().double(), torch.from_numpy(b).cuda().double()
         tol = parity.RTOL * b.abs() + atol * b.abs().max()
         return float(((a - b).abs() / tol).max())
 
-    atol = parity.ATOL_REL
-    assert viol(ours["feature_map"], ref["feature_map"]) <= 1.0
-    atol = parity.GRAD_ATOL_REL
-    for k in ("means3D", "means2D", "sh", "semantic_feature", "opacities", "scales", "rotations"):
-        assert viol(ours["grads"][k], ref["grads"][k]) <= 1.0, k
+    worst = {}
+    if sc.C:
+        worst["feature_map"] = viol(ours["feature_map"], ref["feature_map"], parity.ATOL_REL)
+    if with_grads:
+        for k in ("means3D", "means2D", "sh", "semantic_feature", "opacities", "scales", "rotations"):
+            if k in ours["grads"]:
+                worst["grad_" + k] = viol(ours["grads"][k], ref["grads"][k], parity.GRAD_ATOL_REL)
+    print(f"[{label}] V={int((ours['radii'] > 0).sum())} R={int(ours['num_rendered'])} worst viol per tensor: "
+          + ", ".join(f"{k}={v:.3g}" for k, v in worst.items()))
+    for k, v in worst.items():
+        assert v <= 1.0, (k, v)
+
+
+def test_c3_full_size_vs_reference(c3_scene):
+    """BASELINE.json's metric configuration itself: 1M Gaussians, 1080p, C=128 (device-side comparison)."""
+    _full_size_vs_reference(c3_scene, True, "c3")
+
+
+def test_c4_full_size_vs_reference():
+    """BASELINE.json configs[3]: 1M Gaussians, 1080p, C=256 (two 128-channel chunks per tile), forward + backward."""
+    _full_size_vs_reference(scenegen.make_config("c4", views=1), True, "c4")
+
+
+def test_c5_forward_vs_reference():
+    """BASELINE.json configs[4]: 5M Gaussians, 3840x2160, C=64, forward only (R ~ 16M instances, 47-bit sort keys)."""
+    _full_size_vs_reference(scenegen.make_config("c5"), False, "c5")
 
 
 def test_c3_structural_properties(c3_scene):

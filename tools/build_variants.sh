@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build experiment variants of libf3dgs_b200.so: tools/build_variants.sh name1 "flags1" name2 "flags2" ...
-# -> feature-3dgs_b200/variants/<name>/libf3dgs_b200.so (git-ignored); run with tools/with_variant.sh <name> <cmd>.
+# -> feature-3dgs_b200/variants/<name>/libf3dgs_b200.so (git-ignored).
 set -e
 cd "$(dirname "$0")/.."
 python feature-3dgs_b200/build.py > /dev/null 2>&1   # base objects up to date
