@@ -18,8 +18,9 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libf3dgs_b200.so")
 EXT = os.path.join(PKG, "diff_gaussian_rasterization", "_C" + sysconfig.get_config_var("EXT_SUFFIX"))
-CU = ["api.cu", "preprocess.cu", "binning.cu", "composite_fwd.cu", "composite_bwd.cu", "composite_split.cu"]
-HDRS = ["common.cuh", "kernels.h", "composite_common.cuh", os.path.join(ROOT, "include", "f3dgs_b200.h")]
+CU = ["api.cu", "preprocess.cu", "binning.cu", "composite_fwd.cu", "composite_bwd.cu", "composite_split.cu",
+      "composite_fwd_tc.cu"]
+HDRS = ["common.cuh", "kernels.h", "composite_common.cuh", "tc_common.cuh", os.path.join(ROOT, "include", "f3dgs_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 NVCC_FLAGS += os.environ.get("F3DGS_EXTRA_NVCC_FLAGS", "").split()  # experiments: -DF3DGS_STAGES=6 -DF3DGS_WSLOTS=3 ...

@@ -18,6 +18,10 @@
 #include "../../include/f3dgs_b200.h"
 #include "kernels.h"
 
+#ifndef F3DGS_TC_DEFAULT
+#define F3DGS_TC_DEFAULT 0
+#endif
+
 namespace f3dgs {
 std::atomic<unsigned long long> g_launches{0};
 }
@@ -126,6 +130,16 @@ inline int split_mode(int C) {
         on = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
     }
     return C > 0 ? on : 0;
+}
+
+// Tensor-core feature contraction (composite_fwd_tc.cu).  F3DGS_TC=0|1 overrides the default per process (experiments).
+inline bool tc_mode(int C, const float* features) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("F3DGS_TC");
+        on = e ? (e[0] == '1' ? 1 : 0) : F3DGS_TC_DEFAULT;
+    }
+    return on && C > 64 && C % 4 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0;
 }
 
 inline int bit_length(uint32_t n) {
@@ -338,6 +352,9 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
             if (e == cudaSuccess)
                 e = launch_feature_fwd(vp, ranges, list_w, list_meta, list_cnt, semantic_feature, out_feature_map,
                                        counters + 32, stream);
+        } else if (tc_mode(C, semantic_feature)) {
+            e = launch_composite_fwd_tc(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
+                                        out_color, out_feature_map, out_depth, counters, stream);
         } else {
             e = launch_composite_fwd(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
                                      out_color, out_feature_map, out_depth, counters, stream);
@@ -348,31 +365,48 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     return R;
 }
 
-int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, int width, int height,
-                   const float* means3D, const float* shs, const float* colors_precomp,
-                   const float* semantic_feature, const float* scales, float scale_modifier,
-                   const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
-                   const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
-                   const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
-                   const float* dL_dpix, const float* dL_dfeaturepix, const float* dL_depths, float* dL_dmean2D,
-                   float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dsemantic_feature,
-                   float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-                   float* dL_dz, int debug, void* cuda_stream) {
-    (void)semantic_feature;  // not needed: dL/dfeature depends only on the blend weights (SURVEY D.1/D.2)
-    (void)colors_precomp;    // colours were copied into the per-Gaussian records by the forward
-    t_error.clear();
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
+}  // extern "C"
+
+namespace {
+
+struct ScratchLayout {  // per-view intermediates of the accumulating backward (all zeroed per call)
+    size_t mean2D, conic, dz, color, cov3D, bytes;
+    explicit ScratchLayout(size_t P) {
+        size_t o = 0;
+        mean2D = o;  o = align_up(o + P * 3 * 4);
+        conic = o;   o = align_up(o + P * 4 * 4);
+        dz = o;      o = align_up(o + P * 4);
+        color = o;   o = align_up(o + P * 3 * 4);
+        cov3D = o;   o = align_up(o + P * 6 * 4);
+        bytes = o;
+    }
+};
+
+// Shared body of f3dgs_backward (accumulate = false: the reference's assign-into-zeroed-buffers contract) and
+// f3dgs_backward_accum (accumulate = true: += into the caller's per-parameter gradient buffers).
+int backward_impl(const char* who, bool accumulate, int P, int D, int M, int R, int C, const float* background, int width,
+                  int height, const float* means3D, const float* shs, const float* scales, float scale_modifier,
+                  const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                  const float* cam_pos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                  char* binning_buffer, char* image_buffer, const float* dL_dpix, const float* dL_dfeaturepix,
+                  const float* dL_depths, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                  float* dL_dsemantic_feature, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                  float* dL_drot, float* dL_dz, float* grad_accum, float* denom, cudaEvent_t composite_done, int debug,
+                  cudaStream_t stream) {
+    const std::string w(who);
     if (P < 0 || width <= 0 || height <= 0 || C < 0 || C > F3DGS_MAX_FEATURE_DIM || R < 0)
-        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: bad sizes");
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, w + ": bad sizes");
     if (P == 0) return 0;
     if (!geom_buffer || !binning_buffer || !image_buffer)
-        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: missing forward buffers");
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, w + ": missing forward buffers");
     if (!dL_dpix || !dL_depths || (C > 0 && (!dL_dfeaturepix || !dL_dsemantic_feature)) || !dL_dmean2D ||
         !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dz)
-        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: NULL gradient pointer");
-    if (shs && !dL_dsh) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: shs given but dL_dsh NULL");
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, w + ": NULL gradient pointer");
+    if (shs && !dL_dsh) return fail(F3DGS_ERR_INVALID_ARGUMENT, w + ": shs given but dL_dsh NULL");
     if (scales && (!rotations || !dL_dscale || !dL_drot))
-        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward: scales given but rotations/dL_dscale/dL_drot NULL");
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, w + ": scales given but rotations/dL_dscale/dL_drot NULL");
+    if ((grad_accum == nullptr) != (denom == nullptr))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, w + ": grad_accum and denom go together");
 
     const ViewParams vp = make_view(P, D, M, C, width, height, tan_fovx, tan_fovy, scale_modifier, viewmatrix,
                                     projmatrix, cam_pos);
@@ -419,12 +453,77 @@ int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, i
     }
     if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("composite_bwd launch: ") + cudaGetErrorString(e));
     STAGE_CHECK("composite_bwd");
+    if (composite_done) CUDA_TRY(cudaEventRecord(composite_done, stream));
     {
         StageTimer t(F3DGS_STAGE_PREPROCESS_BWD, stream);
         launch_preprocess_bwd(vp, means3D, radii, shs, clamped, scales, rotations, cov3d, dL_dmean2D, dL_dconic,
-                              dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, stream);
+                              dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, stream, accumulate,
+                              grad_accum, denom);
     }
     STAGE_CHECK("preprocess_bwd");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int f3dgs_backward(int P, int D, int M, int R, int C, const float* background, int width, int height,
+                   const float* means3D, const float* shs, const float* colors_precomp,
+                   const float* semantic_feature, const float* scales, float scale_modifier,
+                   const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                   const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                   const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                   const float* dL_dpix, const float* dL_dfeaturepix, const float* dL_depths, float* dL_dmean2D,
+                   float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dsemantic_feature,
+                   float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                   float* dL_dz, int debug, void* cuda_stream) {
+    (void)semantic_feature;  // not needed: dL/dfeature depends only on the blend weights (SURVEY D.1/D.2)
+    (void)colors_precomp;    // colours were copied into the per-Gaussian records by the forward
+    t_error.clear();
+    return backward_impl("f3dgs_backward", false, P, D, M, R, C, background, width, height, means3D, shs, scales,
+                         scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+                         radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dfeaturepix, dL_depths, dL_dmean2D,
+                         dL_dconic, dL_dopacity, dL_dcolor, dL_dsemantic_feature, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale,
+                         dL_drot, dL_dz, nullptr, nullptr, nullptr, debug, (cudaStream_t)cuda_stream);
+}
+
+size_t f3dgs_backward_scratch_bytes(int P) { return P > 0 ? ScratchLayout((size_t)P).bytes : 0; }
+
+int f3dgs_backward_accum(int P, int D, int M, int R, int C, const float* background, int width, int height,
+                         const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                         float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                         const float* dL_dpix, const float* dL_dfeaturepix, const float* dL_depths, char* scratch,
+                         float* dL_dopacity, float* dL_dcolors_precomp, float* dL_dsemantic_feature, float* dL_dmean3D,
+                         float* dL_dcov3D_precomp, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                         float* dL_dmean2D_out, float* grad_accum, float* denom, void* composite_done_event, int debug,
+                         void* cuda_stream) {
+    t_error.clear();
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (P <= 0) return P == 0 ? 0 : fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward_accum: bad sizes");
+    if (!scratch) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_backward_accum: NULL scratch");
+    if ((colors_precomp != nullptr) != (dL_dcolors_precomp != nullptr) ||
+        (cov3D_precomp != nullptr) != (dL_dcov3D_precomp != nullptr))
+        return fail(F3DGS_ERR_INVALID_ARGUMENT,
+                    "f3dgs_backward_accum: dL_dcolors_precomp / dL_dcov3D_precomp go with colors_precomp / cov3D_precomp");
+    const ScratchLayout sl((size_t)P);
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, sl.bytes, stream));
+    float* m2d = reinterpret_cast<float*>(scratch + sl.mean2D);
+    // colours / cov3D are intermediates unless they are inputs of the caller (then their gradients accumulate)
+    float* dcol = dL_dcolors_precomp ? dL_dcolors_precomp : reinterpret_cast<float*>(scratch + sl.color);
+    float* dcov = dL_dcov3D_precomp ? dL_dcov3D_precomp : reinterpret_cast<float*>(scratch + sl.cov3D);
+    const int rc = backward_impl(
+        "f3dgs_backward_accum", true, P, D, M, R, C, background, width, height, means3D, shs, scales, scale_modifier,
+        rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, radii, geom_buffer,
+        binning_buffer, image_buffer, dL_dpix, dL_dfeaturepix, dL_depths, m2d,
+        reinterpret_cast<float*>(scratch + sl.conic), dL_dopacity, dcol, dL_dsemantic_feature, dL_dmean3D, dcov, dL_dsh,
+        dL_dscale, dL_drot, reinterpret_cast<float*>(scratch + sl.dz), grad_accum, denom,
+        (cudaEvent_t)composite_done_event, debug, stream);
+    if (rc < 0) return rc;
+    if (dL_dmean2D_out)
+        CUDA_TRY(cudaMemcpyAsync(dL_dmean2D_out, m2d, (size_t)P * 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     return 0;
 }
 

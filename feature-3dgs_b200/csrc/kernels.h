@@ -33,7 +33,8 @@ void launch_preprocess_bwd(const ViewParams& vp, const float* means3D, const int
                            const uint8_t* clamped, const float* scales, const float* rotations,
                            const float* cov3D, const float* dL_dmean2D, const float* dL_dconic,
                            float* dL_dmean3D, const float* dL_dcolor, float* dL_dcov3D, float* dL_dsh,
-                           float* dL_dscale, float* dL_drot, const float* dL_dz, cudaStream_t s);
+                           float* dL_dscale, float* dL_drot, const float* dL_dz, cudaStream_t s,
+                           bool accumulate = false, float* grad_accum = nullptr, float* denom = nullptr);
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                          cudaStream_t s);
@@ -50,6 +51,13 @@ cudaError_t launch_composite_fwd(const ViewParams& vp, const uint2* ranges, cons
                                  const SplatRec* rec, const float* features, const float* bg,
                                  float* final_T, uint32_t* n_contrib, float* out_color,
                                  float* out_feature, float* out_depth, int* work_counter, cudaStream_t s);
+
+// composite_fwd_tc.cu: the same contract with the feature contraction on the tensor cores (tcgen05, 3xTF32);
+// needs C % 4 == 0 and a 16-byte aligned feature matrix
+cudaError_t launch_composite_fwd_tc(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
+                                    const SplatRec* rec, const float* features, const float* bg,
+                                    float* final_T, uint32_t* n_contrib, float* out_color,
+                                    float* out_feature, float* out_depth, int* work_counter, cudaStream_t s);
 
 // alpha pass of the two-pass mode (composite_split.cu): the C = 0 forward that also writes the per-block instance lists
 cudaError_t launch_composite_fwd_emit(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,

@@ -276,6 +276,17 @@ __device__ __forceinline__ F3 dnormvdv3(F3 v, F3 dv) {  // reference auxiliary.h
     return o;
 }
 
+// ACCUM = false: the reference's contract -- gradients are ASSIGNED (backward.cu:273, :217-232, :48-97, :323-340) into
+// zero-filled buffers.  ACCUM = true (view batches, f3dgs_backward_accum): every per-parameter gradient is ADDED to what
+// is already there (each Gaussian is written by exactly one thread: plain read-modify-write, no atomics), and the
+// densification statistics of scene/gaussian_model.py:436-438 are folded in.
+template <bool ACCUM>
+__device__ __forceinline__ void put(float* __restrict__ dst, float v) {
+    if (ACCUM) *dst += v;
+    else *dst = v;
+}
+
+template <bool ACCUM>
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const int* __restrict__ radii,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
@@ -284,9 +295,14 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
                       const float* __restrict__ dL_dconic, float* __restrict__ dL_dmean3D,
                       const float* __restrict__ dL_dcolor, float* __restrict__ dL_dcov3D,
                       float* __restrict__ dL_dsh, float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
-                      const float* __restrict__ dL_dz) {
+                      const float* __restrict__ dL_dz, float* __restrict__ grad_accum, float* __restrict__ vis_count) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= vp.P || !(radii[idx] > 0)) return;
+    if (ACCUM && grad_accum != nullptr) {
+        const float ux = dL_dmean2D[3 * idx], uy = dL_dmean2D[3 * idx + 1];
+        grad_accum[idx] += sqrtf(ux * ux + uy * uy);
+        vis_count[idx] += 1.0f;
+    }
     const float* vm = vp.viewmatrix;
     const float* proj = vp.projmatrix;
     const float mx = means3D[3 * idx], my = means3D[3 * idx + 1], mz = means3D[3 * idx + 2];
@@ -321,7 +337,7 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
         for (int i = 0; i < 6; i++) dcov[i] = 0;
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = dcov[i];
+    for (int i = 0; i < 6; i++) put<ACCUM>(dL_dcov3D + 6 * idx + i, dcov[i]);
 
     // Vrk rows (symmetric): V0 = (cv0,cv1,cv2), V1 = (cv1,cv3,cv4), V2 = (cv2,cv4,cv5)
     const float T0V0 = T00 * cv[0] + T01 * cv[1] + T02 * cv[2];
@@ -390,9 +406,9 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
 #define WR(k, coef)                                                  \
     do {                                                             \
         const float cf_ = (coef);                                    \
-        dsh[3 * (k)] = cf_ * dRGB[0];                                \
-        dsh[3 * (k) + 1] = cf_ * dRGB[1];                            \
-        dsh[3 * (k) + 2] = cf_ * dRGB[2];                            \
+        put<ACCUM>(dsh + 3 * (k), cf_ * dRGB[0]);                    \
+        put<ACCUM>(dsh + 3 * (k) + 1, cf_ * dRGB[1]);                \
+        put<ACCUM>(dsh + 3 * (k) + 2, cf_ * dRGB[2]);                \
     } while (0)
         WR(0, kSH_C0);
         if (deg > 0) {
@@ -456,9 +472,9 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
         const F3 dm = dnormvdv3(dir_orig, F3{ddx, ddy, ddz});
         gx += dm.x; gy += dm.y; gz += dm.z;
     }
-    dL_dmean3D[3 * idx] = gx;
-    dL_dmean3D[3 * idx + 1] = gy;
-    dL_dmean3D[3 * idx + 2] = gz;
+    put<ACCUM>(dL_dmean3D + 3 * idx, gx);
+    put<ACCUM>(dL_dmean3D + 3 * idx + 1, gy);
+    put<ACCUM>(dL_dmean3D + 3 * idx + 2, gz);
 
     // ---- cov3D -> scale / rotation (reference backward.cu:278-341)
     if (scales != nullptr) {
@@ -495,7 +511,7 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
             for (int rr = 0; rr < 3; rr++) dMt[cc][rr] = dM[rr][cc];
 #pragma unroll
         for (int k = 0; k < 3; k++)
-            dL_dscale[3 * idx + k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
+            put<ACCUM>(dL_dscale + 3 * idx + k, R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2]);
 #pragma unroll
         for (int k = 0; k < 3; k++)
 #pragma unroll
@@ -508,6 +524,10 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
                4 * y * (dMt[2][2] + dMt[0][0]);
         dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
                4 * z * (dMt[1][1] + dMt[0][0]);
+        if (ACCUM) {
+            const float4 o = reinterpret_cast<float4*>(dL_drot)[idx];
+            dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+        }
         reinterpret_cast<float4*>(dL_drot)[idx] = dq;
     }
 }
@@ -529,11 +549,17 @@ void launch_preprocess_bwd(const ViewParams& vp, const float* means3D, const int
                            const uint8_t* clamped, const float* scales, const float* rotations,
                            const float* cov3D, const float* dL_dmean2D, const float* dL_dconic,
                            float* dL_dmean3D, const float* dL_dcolor, float* dL_dcov3D, float* dL_dsh,
-                           float* dL_dscale, float* dL_drot, const float* dL_dz, cudaStream_t s) {
+                           float* dL_dscale, float* dL_drot, const float* dL_dz, cudaStream_t s, bool accumulate,
+                           float* grad_accum, float* denom) {
     if (vp.P <= 0) return;
-    preprocess_bwd_kernel<<<(vp.P + 255) / 256, 256, 0, s>>>(vp, means3D, radii, shs, clamped, scales, rotations,
-                                                           cov3D, dL_dmean2D, dL_dconic, dL_dmean3D, dL_dcolor,
-                                                           dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz);
+    if (accumulate)
+        preprocess_bwd_kernel<true><<<(vp.P + 255) / 256, 256, 0, s>>>(
+            vp, means3D, radii, shs, clamped, scales, rotations, cov3D, dL_dmean2D, dL_dconic, dL_dmean3D, dL_dcolor,
+            dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, grad_accum, denom);
+    else
+        preprocess_bwd_kernel<false><<<(vp.P + 255) / 256, 256, 0, s>>>(
+            vp, means3D, radii, shs, clamped, scales, rotations, cov3D, dL_dmean2D, dL_dconic, dL_dmean3D, dL_dcolor,
+            dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, nullptr, nullptr);
     g_launches++;
 }
 

@@ -172,6 +172,65 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
                            dL_dscales, dL_drotations);
 }
 
+// Accumulating backward for view batches (additive to the reference module): gradients are ADDED into the tensors the
+// caller passes (typically views of one flat gradient buffer, see diff_gaussian_rasterization/parallel.py); nothing is
+// allocated besides one cached scratch tensor per device.  Undefined / empty tensors stand for "not an input".
+void RasterizeGaussiansBackwardAccumCUDA(
+    const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+    const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations, const float scale_modifier,
+    const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+    const float tan_fovx, const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_feature,
+    const torch::Tensor& dL_dout_depth, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+    const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+    torch::Tensor scratch, torch::Tensor g_means3D, torch::Tensor g_sh, torch::Tensor g_colors,
+    torch::Tensor g_semantic_feature, torch::Tensor g_opacities, torch::Tensor g_scales, torch::Tensor g_rotations,
+    torch::Tensor g_cov3D, torch::Tensor g_means2D_out, torch::Tensor grad_accum, torch::Tensor denom,
+    const int64_t composite_done_event, const bool debug) {
+    TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor (this build has no CPU path)");
+    const c10::cuda::CUDAGuard guard(means3D.device());
+    const auto dev = means3D.device();
+    const int P = means3D.size(0);
+    if (P == 0) return;
+    const int H = dL_dout_color.size(1), W = dL_dout_color.size(2);
+    int M = 0;
+    if (sh.defined() && sh.numel() != 0) M = sh.size(1);
+    const int C = (dL_dout_feature.defined() && dL_dout_feature.dim() == 3) ? (int)dL_dout_feature.size(0) : 0;
+    auto gcheck = [&](const torch::Tensor& t, int64_t numel, const char* name) -> float* {
+        if (!t.defined() || t.numel() == 0) return nullptr;
+        TORCH_CHECK(t.is_cuda() && t.device() == dev && t.scalar_type() == torch::kFloat32 && t.is_contiguous() &&
+                        t.numel() == numel, name, " must be a contiguous float32 CUDA tensor with ", numel, " elements");
+        return t.data_ptr<float>();
+    };
+    auto bg = prep(background, dev, "bg"), m3 = prep(means3D, dev, "means3D");
+    auto col = prep(colors, dev, "colors_precomp");
+    auto sc = prep(scales, dev, "scales"), rot = prep(rotations, dev, "rotations");
+    auto cov = prep(cov3D_precomp, dev, "cov3D_precomp");
+    auto vm = prep(viewmatrix, dev, "viewmatrix"), pm = prep(projmatrix, dev, "projmatrix");
+    auto shc = prep(sh, dev, "shs"), cp = prep(campos, dev, "campos");
+    auto gc = prep(dL_dout_color, dev, "grad_out_color"), gd = prep(dL_dout_depth, dev, "grad_out_depth");
+    torch::Tensor gf = C ? prep(dL_dout_feature, dev, "grad_out_feature") : dL_dout_feature;
+    TORCH_CHECK(radii.scalar_type() == torch::kInt32 && radii.is_cuda(), "radii must be int32 CUDA");
+    auto rad = radii.contiguous();
+    const size_t need = f3dgs_backward_scratch_bytes(P);
+    TORCH_CHECK(scratch.defined() && scratch.is_cuda() && scratch.scalar_type() == torch::kByte &&
+                    scratch.is_contiguous() && (size_t)scratch.numel() >= need,
+                "scratch must be a contiguous uint8 CUDA tensor of at least ", need, " bytes");
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    int rc = f3dgs_backward_accum(
+        P, degree, M, R, C, fptr(bg), W, H, fptr(m3), fptr(shc), fptr(col), fptr(sc), scale_modifier, fptr(rot), fptr(cov),
+        fptr(vm), fptr(pm), fptr(cp), tan_fovx, tan_fovy, rad.data_ptr<int>(),
+        reinterpret_cast<char*>(geomBuffer.data_ptr()), reinterpret_cast<char*>(binningBuffer.data_ptr()),
+        reinterpret_cast<char*>(imageBuffer.data_ptr()), fptr(gc), C ? fptr(gf) : nullptr, fptr(gd),
+        reinterpret_cast<char*>(scratch.data_ptr()), gcheck(g_opacities, P, "g_opacities"),
+        gcheck(g_colors, (int64_t)P * 3, "g_colors_precomp"), gcheck(g_semantic_feature, (int64_t)P * C, "g_semantic_feature"),
+        gcheck(g_means3D, (int64_t)P * 3, "g_means3D"), gcheck(g_cov3D, (int64_t)P * 6, "g_cov3D_precomp"),
+        gcheck(g_sh, (int64_t)P * M * 3, "g_sh"), gcheck(g_scales, (int64_t)P * 3, "g_scales"),
+        gcheck(g_rotations, (int64_t)P * 4, "g_rotations"), gcheck(g_means2D_out, (int64_t)P * 3, "g_means2D_out"),
+        gcheck(grad_accum, P, "grad_accum"), gcheck(denom, P, "denom"),
+        reinterpret_cast<void*>(static_cast<intptr_t>(composite_done_event)), debug ? 1 : 0, (void*)stream);
+    check_rc(rc, "f3dgs_backward_accum");
+}
+
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix) {
     TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor (this build has no CPU path)");
     const c10::cuda::CUDAGuard guard(means3D.device());
@@ -214,6 +273,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("mark_visible", &markVisible);
+    m.def("rasterize_gaussians_backward_accum", &RasterizeGaussiansBackwardAccumCUDA);
+    m.def("backward_scratch_bytes", [](int P) { return (unsigned long long)f3dgs_backward_scratch_bytes(P); });
     m.def("debug_views", &debugViews);
     m.def("launch_count", []() { return (unsigned long long)f3dgs_launch_count(); });
     m.def("abi_version", []() { return f3dgs_abi_version(); });

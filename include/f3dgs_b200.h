@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define F3DGS_ABI_VERSION 1
+#define F3DGS_ABI_VERSION 2
 #define F3DGS_MAX_FEATURE_DIM 4096
 #define F3DGS_TILE 16 /* BLOCK_X == BLOCK_Y == 16, reference config.h:18-19 */
 
@@ -99,6 +99,39 @@ int f3dgs_backward(int P, int D, int M, int R, int C,
                    float* dL_dsemantic_feature, float* dL_dmean3D, float* dL_dcov3D,
                    float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_dz,
                    int debug, void* cuda_stream);
+
+/* ---- accumulating backward for view batches (additive: the reference ASSIGNS per-view gradients into freshly
+ * zero-filled tensors, rasterize_points.cu:163-173, backward.cu:273, and leaves the sum over views to autograd) ----
+ * Same inputs as f3dgs_backward.  Differences:
+ *   - every per-parameter gradient (dL_dopacity [P], dL_dsemantic_feature [P,C], dL_dmean3D [P,3], dL_dsh [P,M,3],
+ *     dL_dscale [P,3], dL_drot [P,4], and dL_dcolors_precomp [P,3] / dL_dcov3D_precomp [P,6] when those are the inputs,
+ *     NULL otherwise) is ACCUMULATED (+=): the caller zeroes them once per step, e.g. as slices of one flat buffer that
+ *     is then all-reduced once;
+ *   - the per-view intermediates (screen-space mean, conic, depth, colour and covariance gradients) live in `scratch`
+ *     (f3dgs_backward_scratch_bytes(P) bytes of device memory, 256-byte aligned), which the call zeroes itself;
+ *   - dL_dmean2D_out (optional, [P,3]) receives this view's screen-space gradient (the reference's
+ *     viewspace_point_tensor.grad);
+ *   - grad_accum / denom (optional, both or neither, [P]): the densification statistics of the reference training loop
+ *     (scene/gaussian_model.py:436-438): for radii > 0, grad_accum += ||dL_dmean2D.xy||, denom += 1;
+ *   - composite_done_event (optional cudaEvent_t): recorded on the stream after the backward composite kernel, i.e. when
+ *     dL_dsemantic_feature and dL_dopacity of this view are complete (the backward preprocess does not touch them), so
+ *     that a collective on that bucket can start on another stream while the preprocess still runs.
+ */
+size_t f3dgs_backward_scratch_bytes(int P);
+int f3dgs_backward_accum(int P, int D, int M, int R, int C,
+                         const float* background, int width, int height,
+                         const float* means3D, const float* shs, const float* colors_precomp,
+                         const float* scales, float scale_modifier, const float* rotations,
+                         const float* cov3D_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                         float tan_fovx, float tan_fovy, const int* radii,
+                         char* geom_buffer, char* binning_buffer, char* image_buffer,
+                         const float* dL_dpix, const float* dL_dfeaturepix, const float* dL_depths,
+                         char* scratch,
+                         float* dL_dopacity, float* dL_dcolors_precomp, float* dL_dsemantic_feature,
+                         float* dL_dmean3D, float* dL_dcov3D_precomp, float* dL_dsh, float* dL_dscale,
+                         float* dL_drot, float* dL_dmean2D_out, float* grad_accum, float* denom,
+                         void* composite_done_event, int debug, void* cuda_stream);
 
 /* ---- markVisible: reference rasterizer_impl.cu:141-153 (checkFrustum :54-66) --------------
  * present[i] = (view-space z of means3D[i] > 0.2).  `present` is P bytes (0/1). */

@@ -52,7 +52,7 @@ def test_no_torch_or_python_dependency(built):
 
 def test_abi_version_and_launch_counter(lib):
     lib.f3dgs_launch_count.restype = ctypes.c_ulonglong
-    assert lib.f3dgs_abi_version() == 1
+    assert lib.f3dgs_abi_version() == 2
     assert lib.f3dgs_launch_count() == 0  # nothing launched in a CPU-only process
 
 

@@ -393,3 +393,54 @@ def test_c3_feature_linearity_and_width_independence(c3_scene):
     c = parity.run_ours(sc0, cam)
     for k in ("color", "depth", "final_T", "n_contrib", "point_list", "ranges", "radii"):
         assert np.array_equal(a[k], c[k]), k
+
+
+# ------------------------------------------------------------------------------------------- view batches
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_view_batch_accumulates_like_autograd(name):
+    """ViewBatch (f3dgs_backward_accum: gradients ADDED in-kernel into one flat buffer, densification statistics folded
+    in) against the sum over views of the per-view gradients from the reference-compatible autograd API."""
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from diff_gaussian_rasterization.parallel import ViewBatch
+
+    sc = scenegen.make_config(name, views=3)
+    dev = "cuda"
+    t = scenegen.to_torch(sc, dev, requires_grad=True)
+    cam0 = sc.cameras[0]
+    ups = [[torch.from_numpy(g).to(dev) for g in scenegen.upstream_grads(cam0.image_height, cam0.image_width, sc.C, seed=50 + v)]
+           for v in range(3)]
+    names = ("means3D", "scales", "rotations", "opacities", "shs", "semantic_feature")
+    want = {k: torch.zeros_like(t[k]) for k in names}
+    accum, denom = torch.zeros(sc.P, device=dev), torch.zeros(sc.P, device=dev)
+    outs = []
+    for v, cam in enumerate(sc.cameras):
+        rs = GaussianRasterizationSettings(**scenegen.settings_kwargs(sc, cam, dev))
+        m2 = torch.zeros_like(t["means3D"], requires_grad=True)
+        color, feat, radii, depth = GaussianRasterizer(rs)(
+            means3D=t["means3D"], means2D=m2, opacities=t["opacities"], shs=t["shs"],
+            semantic_feature=t["semantic_feature"], scales=t["scales"], rotations=t["rotations"])
+        torch.autograd.backward([color, depth, feat], [ups[v][0], ups[v][2], ups[v][1]])
+        for k in names:
+            want[k] += t[k].grad
+            t[k].grad = None
+        vis = radii > 0
+        accum[vis] += m2.grad[vis, :2].norm(dim=-1)   # scene/gaussian_model.py:436-438
+        denom[vis] += 1
+        outs.append((color.detach(), feat.detach(), depth.detach(), m2.grad.clone()))
+
+    vb = ViewBatch({k: t[k].detach() for k in names})
+    vb.zero_()
+    for v, cam in enumerate(sc.cameras):
+        rs = GaussianRasterizationSettings(**scenegen.settings_kwargs(sc, cam, dev))
+        color, feat, radii, depth, ctx = vb.forward(rs)
+        assert torch.equal(color, outs[v][0]) and torch.equal(depth, outs[v][2]) and torch.equal(feat, outs[v][1])
+        m2 = torch.empty(sc.P, 3, device=dev)
+        vb.backward(ctx, ups[v][0], ups[v][1], ups[v][2], means2D_out=m2, last=(v == 2))
+        assert parity.float_mismatch(m2.cpu().numpy(), outs[v][3].cpu().numpy(), atol_rel=parity.GRAD_ATOL_REL)[0] <= 1.0
+    vb.all_reduce()  # no process group: a no-op that must leave the buffer intact
+    for k in names:
+        r = parity.float_mismatch(vb.grads[k].cpu().numpy(), want[k].cpu().numpy(), atol_rel=parity.GRAD_ATOL_REL)[0]
+        assert r <= 1.0, (k, r)
+    assert torch.equal(vb.denom, denom)
+    assert parity.float_mismatch(vb.grad_accum.cpu().numpy(), accum.cpu().numpy(), atol_rel=parity.GRAD_ATOL_REL)[0] <= 1.0

@@ -18,13 +18,13 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
     return d;
 }
 __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -64,7 +64,10 @@ struct Params {
     int mode;         // 0, 1, 2
     int terms;        // 1: hi*hi only, 3: compensated
     int swap_lbo_sbo;
+    int variant;      // mode 0 only: 0 = SW128 (16-byte chunks ^ (k & 7), atoms of 8 k);  1 = SW128_BASE32B (32-byte chunks ^ (k & 3), atoms of 4 k)
 };
+// float index of element c (0..31) of row r for the 32-byte-granular swizzle of MN-major 32-bit operands
+__device__ __forceinline__ int sw128_32b(int r, int c) { return r * 32 + ((((c >> 3) ^ (r & 3)) << 3) | (c & 7)); }
 
 constexpr int KF = 32;  // instances per stage in case 0
 extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -96,14 +99,14 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
         for (int i = tid; i < KF * 128; i += 128) {
             const int k = i / 128, c = i % 128;
             const float v = p.A[k * 128 + c], h = tf32_hi(v);
-            const int o = (c >> 5) * (KF * 32) + sw128(k, c & 31);
+            const int o = (c >> 5) * (KF * 32) + (p.variant ? sw128_32b(k, c & 31) : sw128(k, c & 31));
             Ahi[o] = h;
             Alo[o] = v - h;
         }
         for (int i = tid; i < KF * 256; i += 128) {
             const int k = i / 256, c = i % 256;
             const float v = p.B[k * 256 + c], h = tf32_hi(v);
-            const int o = (c >> 5) * (KF * 32) + sw128(k, c & 31);
+            const int o = (c >> 5) * (KF * 32) + (p.variant ? sw128_32b(k, c & 31) : sw128(k, c & 31));
             Bhi[o] = h;
             Blo[o] = v - h;
         }
@@ -112,12 +115,13 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t idesc = make_idesc(128, 256, 1, 1);
-            uint32_t lbo = KF * 128, sbo = 1024;  // MN-major: LBO = next 32-element block along MN, SBO = next 8 k
+            const uint32_t lt = p.variant ? 1u : 2u;
+            uint32_t lbo = KF * 128, sbo = p.variant ? 512 : 1024;  // MN-major: LBO = next 32-element block along MN, SBO = next k atom
             if (p.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
             uint32_t acc = 0;
             for (int g = 0; g < KF / 8; g++) {
-                const uint64_t ah = make_desc(smem_u32(Ahi) + g * 1024, lbo, sbo), al = make_desc(smem_u32(Alo) + g * 1024, lbo, sbo);
-                const uint64_t bh = make_desc(smem_u32(Bhi) + g * 1024, lbo, sbo), bl = make_desc(smem_u32(Blo) + g * 1024, lbo, sbo);
+                const uint64_t ah = make_desc(smem_u32(Ahi) + g * 1024, lbo, sbo, lt), al = make_desc(smem_u32(Alo) + g * 1024, lbo, sbo, lt);
+                const uint64_t bh = make_desc(smem_u32(Bhi) + g * 1024, lbo, sbo, lt), bl = make_desc(smem_u32(Blo) + g * 1024, lbo, sbo, lt);
                 mma_ss(tmem, ah, bh, idesc, acc);
                 acc = 1;
                 if (p.terms == 3) {
@@ -221,7 +225,8 @@ int main() {
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int mode = 0; mode < 3; mode++)
         for (int terms = 1; terms <= 3; terms += 2)
-            for (int swap = 0; swap < 2; swap++) {
+            for (int swap = 0; swap < 2; swap++)
+                for (int variant = 0; variant < (mode == 0 ? 2 : 1); variant++) {
                 const int M = 128, N = mode == 0 ? 256 : 32, K = mode == 0 ? KF : 256;
                 std::vector<float> A, B;
                 srand(7 + mode);
@@ -246,7 +251,7 @@ int main() {
                 cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
                 cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
                 cudaMemset(dD, 0xFF, (size_t)M * N * 4);
-                Params p{dA, dB, dD, mode, terms, swap};
+                Params p{dA, dB, dD, mode, terms, swap, variant};
                 probe_kernel<<<1, 128, 200 * 1024>>>(p);
                 cudaError_t e = cudaDeviceSynchronize();
                 std::vector<float> D((size_t)M * N);
@@ -257,8 +262,8 @@ int main() {
                     worst = fmax(worst, err / (mag[i] + 1e-30));
                     worst_abs = fmax(worst_abs, err);
                 }
-                printf("mode %d terms %d swap_lbo_sbo %d: cuda=%s  max |err| / sum|terms| = %.3e  max|err| = %.3e  D[0]=%g ref[0]=%g\n",
-                       mode, terms, swap, cudaGetErrorString(e), worst, worst_abs, D[0], ref[0]);
+                printf("mode %d variant %d terms %d swap_lbo_sbo %d: cuda=%s  max |err| / sum|terms| = %.3e  max|err| = %.3e  D[0]=%g ref[0]=%g\n",
+                       mode, variant, terms, swap, cudaGetErrorString(e), worst, worst_abs, D[0], ref[0]);
                 cudaFree(dA); cudaFree(dB); cudaFree(dD);
                 if (e != cudaSuccess) { printf("aborting after CUDA error\n"); return 1; }
             }

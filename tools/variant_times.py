@@ -126,6 +126,11 @@ def main():
     for name in names:
         os.environ.pop("F3DGS_TIMING", None)
         os.environ.pop("F3DGS_SPLIT", None)
+        os.environ.pop("F3DGS_TC", None)
+        if name.endswith("+tc"):
+            os.environ["F3DGS_TC"] = "1"  # tensor-core feature contraction (read once per library instance)
+        if name.endswith("+notc"):
+            os.environ["F3DGS_TC"] = "0"
         if name.startswith("timing"):
             os.environ["F3DGS_TIMING"] = "1"
         if name.endswith("+split"):
