@@ -144,6 +144,10 @@ def main():
     ap.add_argument("--config", default="c3", choices=list(scenegen.CONFIGS))
     ap.add_argument("--views-per-rank", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--api", default="batch", choices=["batch", "autograd"],
+                    help="ours only: 'batch' = ViewBatch (autograd-free forward + in-kernel gradient accumulation, the "
+                         "framework's own view-batch API); 'autograd' = the reference-compatible GaussianRasterizer autograd API. "
+                         "The line's value/e2e use this API; the other one is measured too and reported under config.")
     ap.add_argument("--batch-views", type=int, default=64,
                     help="config c4 only: size of the view batch sharded over the ranks (BASELINE: 64)")
     ap.add_argument("--l2-flush", action="store_true",
@@ -205,7 +209,7 @@ def main():
 
     if args.impl == "ours":
         from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
-        from diff_gaussian_rasterization.parallel import FlatGradBuffer, shard_views
+        from diff_gaussian_rasterization.parallel import FlatGradBuffer, ViewBatch, shard_views
     else:
         # The reference arm must not map this repo's native libraries: the host-side helpers (flat gradient buffer, view
         # sharding -- pure torch) are loaded by FILE PATH so that the package __init__ (which imports _C) never runs.
@@ -251,6 +255,39 @@ def main():
             semantic_feature=t["semantic_feature"] if C else None, scales=t["scales"], rotations=t["rotations"])
 
     stats = {}
+    use_batch = args.impl == "ours" and args.api == "batch" and not fwd_only
+    if args.impl == "ours" and not fwd_only:
+        vb = ViewBatch({k: t[k].detach() for k in ("means3D", "scales", "rotations", "opacities", "shs", "semantic_feature")})
+
+        def settings_of(cam, packed):
+            return GaussianRasterizationSettings(
+                image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
+                viewmatrix=packed[0:16].view(4, 4), projmatrix=packed[16:32].view(4, 4), sh_degree=scene.sh_degree,
+                campos=packed[32:35], prefiltered=False, debug=False)
+
+        def step_device_batch():
+            vb.zero_()
+            for i, cam in enumerate(cams):
+                color, feat, radii, depth, ctx = vb.forward(settings_of(cam, cam_dev[i]))
+                vb.backward(ctx, gc, gf if C else None, gd, last=(i == len(cams) - 1))
+                stats["radii"] = radii
+            vb.all_reduce()
+
+        def step_e2e_batch():
+            vb.zero_()
+            total = torch.zeros((), device=dev)
+            for i, cam in enumerate(cams):
+                cam_stage[i].copy_(cam_host[i], non_blocking=True)  # H2D of this view's camera
+                color, feat, radii, depth, ctx = vb.forward(settings_of(cam, cam_stage[i]))
+                outs = [color.requires_grad_(), depth.requires_grad_()] + ([feat.requires_grad_()] if C else [])
+                loss = (outs[0] * gc).sum() + (outs[1] * gd).sum()
+                if C:
+                    loss = loss + (outs[2] * gf).sum()
+                loss.backward()  # the user's loss: autograd only over the three rendered maps
+                vb.backward(ctx, color.grad, feat.grad if C else None, depth.grad, last=(i == len(cams) - 1))
+                total = total + loss.detach()
+            vb.all_reduce()
+            return float(total.item())  # D2H read of the step's result
 
     def step_device():
         if fwd_only:
@@ -272,6 +309,7 @@ def main():
 
     h2d_bytes = sum(h.numel() * 4 for h in cam_host)
     cam_stage = [torch.empty_like(d) for d in cam_dev]
+    step_device_autograd = step_device
 
     def step_e2e():
         total = torch.zeros((), device=dev)
@@ -334,14 +372,15 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()  # nvidia-smi takes ~1 s to produce its first row: start before the warm-up
+    main_step = step_device_batch if use_batch else step_device
     for _ in range(args.warmup):
-        step_device()
+        main_step()
     barrier()
     if _C is not None:
         _C.profile_read()
         _C.profile_enable(True)
         launches0 = _C.launch_count()
-    ms_total = timed(step_device, args.steps, 0)
+    ms_total = timed(main_step, args.steps, 0)
     if _C is not None:
         launches = _C.launch_count() - launches0
         _C.profile_enable(False)
@@ -350,8 +389,17 @@ def main():
     value = views_per_step * args.steps / (ms_total / 1000.0)
 
     # ---------------- timed region 2: end to end
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ms_e2e = timed(step_e2e_batch if use_batch else step_e2e, args.steps, max(args.warmup, 3))
     e2e_value = views_per_step * args.steps / (ms_e2e / 1000.0)
+    other_api = None
+    if args.impl == "ours" and not fwd_only:
+        # the other public API, same procedure, for the record
+        o_dev, o_e2e = (step_device_autograd, step_e2e) if use_batch else (step_device_batch, step_e2e_batch)
+        o_ms = timed(o_dev, args.steps, max(args.warmup, 3))
+        o_ms_e2e = timed(o_e2e, args.steps, max(args.warmup, 3))
+        other_api = {"api": "autograd" if use_batch else "batch",
+                     "value": views_per_step * args.steps / (o_ms / 1000.0), "ms_per_step": o_ms / args.steps,
+                     "e2e_value": views_per_step * args.steps / (o_ms_e2e / 1000.0), "e2e_ms_per_step": o_ms_e2e / args.steps}
     if sampler:
         clocks = sampler.stop()  # rows cover warm-up + both timed regions (the GPU is busy throughout)
 
@@ -371,7 +419,10 @@ def main():
                    "parallelism": f"view-sharded dp{world}, 1 grad all-reduce/step" if distributed else "single GPU",
                    "l2": ("explicit flush: 512 MB fill between timed steps, outside the per-step event pairs" if args.l2_flush
                           else "inputs exceed the 126 MB L2 (per view: features P*C*4 B, upstream grads C*H*W*4 B); no explicit flush"),
-                   "api": "GaussianRasterizer autograd API (forward" + ("" if fwd_only else " + torch.autograd.backward") + ")",
+                   "api": ("ViewBatch: _C.rasterize_gaussians forward + in-kernel gradient accumulation "
+                           "(f3dgs_backward_accum) into one flat buffer, densification statistics folded in" if use_batch else
+                           "GaussianRasterizer autograd API (forward" + ("" if fwd_only else " + torch.autograd.backward") + ")"),
+                   "other_api": other_api,
                    "e2e_moves": "per view: 35 floats of camera state from pinned host memory (H2D); per step: the scalar loss "
                                 "(D2H). Gaussian parameters, upstream-gradient weights and rendered maps stay in HBM (model "
                                 "state and loss inputs of a training loop, as in the reference train.py)"},

@@ -18,8 +18,11 @@
 #include "../../include/f3dgs_b200.h"
 #include "kernels.h"
 
+#ifndef F3DGS_BWD2_DEFAULT
+#define F3DGS_BWD2_DEFAULT 1
+#endif
 #ifndef F3DGS_TC_DEFAULT
-#define F3DGS_TC_DEFAULT 0
+#define F3DGS_TC_DEFAULT 1
 #endif
 
 namespace f3dgs {
@@ -104,32 +107,39 @@ struct ImgLayout {
 };
 struct BinLayout {
     size_t point_list, keys, point_list_unsorted, keys_unsorted, fixed_bytes;
-    size_t list_w = 0, list_meta = 0, list_cnt = 0;  // two-pass mode only (composite_split.cu)
-    explicit BinLayout(size_t R, size_t split_tiles = 0) {
+    explicit BinLayout(size_t R) {
         size_t o = 0;
         point_list = o;           o = align_up(o + R * 4);
         keys = o;                 o = align_up(o + R * 8);
         point_list_unsorted = o;  o = align_up(o + R * 4);
         keys_unsorted = o;        o = align_up(o + R * 8);
-        if (split_tiles) {  // per (tile, 8x4 block) instance lists: 8R entries of capacity (block b of a tile owns `len` of them)
-            list_w = o;     o = align_up(o + 8 * R * 32 * sizeof(float));
-            list_meta = o;  o = align_up(o + 8 * R * sizeof(uint2));
-            list_cnt = o;   o = align_up(o + 8 * split_tiles * sizeof(uint32_t));
-        }
         fixed_bytes = o;
     }
 };
 
-// Two-pass composite (alpha pass + feature pass, composite_split.cu): experimental, opt-in per process with F3DGS_SPLIT=1.
-// The forward and the matching backward must see the same setting (the binning buffer layout depends on it).
-// F3DGS_SPLIT=2 additionally runs the two alpha passes with the slim layout (12 warps per CTA, two CTAs per SM).
-inline int split_mode(int C) {
+// Per (tile, 8x4 block) instance lists of the two-kernel backward: 8R entries of capacity (block b of a tile owns `len` of them).
+struct ListLayout {
+    size_t w, meta, cnt, bytes;
+    ListLayout(size_t R, size_t tiles) {
+        size_t o = 0;
+        w = o;     o = align_up(o + 8 * R * 32 * sizeof(float));
+        meta = o;  o = align_up(o + 8 * R * sizeof(uint2));
+        cnt = o;   o = align_up(o + 8 * tiles * sizeof(uint32_t));
+        bytes = o;
+    }
+};
+
+// Two-kernel backward (default): geometric gradients from the alpha-only kernel at two CTAs per SM, which also emits the
+// blend weights per (tile, block); the feature gradient is a second, streaming kernel over those lists
+// (feature_bwd.cu).  Measured at config 3: 2.80 ms against 3.47 ms for the fused kernel (profiles/r02_variants.jsonl).
+// F3DGS_BWD2=0|1 overrides the default per process (A/B runs; both settings are covered by the GPU test-suite).
+inline bool bwd2_mode() {
     static int on = -1;
     if (on < 0) {
-        const char* e = getenv("F3DGS_SPLIT");
-        on = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+        const char* e = getenv("F3DGS_BWD2");
+        on = e ? (e[0] == '1' ? 1 : 0) : F3DGS_BWD2_DEFAULT;
     }
-    return C > 0 ? on : 0;
+    return on != 0;
 }
 
 // Tensor-core feature contraction (composite_fwd_tc.cu).  F3DGS_TC=0|1 overrides the default per process (experiments).
@@ -304,8 +314,7 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     if (R < 0) return fail(F3DGS_ERR_CUDA, "num_rendered overflowed int32");
 
     // ---- binning buffer
-    const int split = split_mode(C);
-    const BinLayout bl((size_t)R, split ? tiles : 0);
+    const BinLayout bl((size_t)R);
     const int end_bit = 32 + bit_length((uint32_t)(tiles > 0 ? tiles - 1 : 0));
     size_t sort_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr,
@@ -342,17 +351,7 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     {
         StageTimer t(F3DGS_STAGE_COMPOSITE_FWD, stream);
         int* counters = reinterpret_cast<int*>(img + il.counters);
-        if (split) {
-            float* list_w = reinterpret_cast<float*>(bin + bl.list_w);
-            uint2* list_meta = reinterpret_cast<uint2*>(bin + bl.list_meta);
-            uint32_t* list_cnt = reinterpret_cast<uint32_t*>(bin + bl.list_cnt);
-            e = (split == 2 ? launch_composite_fwd_emit_slim : launch_composite_fwd_emit)(
-                vp, ranges, point_list, rec, background, final_T, n_contrib, out_color, out_depth, list_w, list_meta,
-                list_cnt, counters, stream);
-            if (e == cudaSuccess)
-                e = launch_feature_fwd(vp, ranges, list_w, list_meta, list_cnt, semantic_feature, out_feature_map,
-                                       counters + 32, stream);
-        } else if (tc_mode(C, semantic_feature)) {
+        if (tc_mode(C, semantic_feature)) {
             e = launch_composite_fwd_tc(vp, ranges, point_list, rec, semantic_feature, background, final_T, n_contrib,
                                         out_color, out_feature_map, out_depth, counters, stream);
         } else {
@@ -413,8 +412,7 @@ int backward_impl(const char* who, bool accumulate, int P, int D, int M, int R, 
     const size_t tiles = (size_t)vp.grid_x * vp.grid_y;
     const GeomLayout gl((size_t)P);
     const ImgLayout il((size_t)width * height, tiles);
-    const int split = split_mode(C);
-    const BinLayout bl((size_t)R, split ? tiles : 0);
+    const BinLayout bl((size_t)R);
     const SplatRec* rec = reinterpret_cast<const SplatRec*>(geom_buffer + gl.rec);
     const float* cov3d = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(geom_buffer + gl.cov3d);
     const uint8_t* clamped = reinterpret_cast<const uint8_t*>(geom_buffer + gl.clamped);
@@ -428,23 +426,41 @@ int backward_impl(const char* who, bool accumulate, int P, int D, int M, int R, 
     {
         StageTimer t(F3DGS_STAGE_COMPOSITE_BWD, stream);
         int* counters = reinterpret_cast<int*>(image_buffer + il.counters);
-        if (split) {
-            // geometric gradients: the C = 0 backward kernel; feature gradient: one more pass over the forward's lists
+        if (bwd2_mode()) {
             ViewParams vg = vp;
             vg.C = 0;
-            if (split == 2)
-                e = launch_composite_bwd_geom_slim(vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,
-                                                   dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dz,
-                                                   counters + 16, stream);
-            else
-                e = launch_composite_bwd(vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, nullptr,
-                                         dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, nullptr, dL_dz,
-                                         counters + 16, stream);
-            if (e == cudaSuccess)
-                e = launch_feature_bwd(vp, ranges, reinterpret_cast<const float*>(binning_buffer + bl.list_w),
-                                       reinterpret_cast<const uint2*>(binning_buffer + bl.list_meta),
-                                       reinterpret_cast<const uint32_t*>(binning_buffer + bl.list_cnt), dL_dfeaturepix,
+            char* lists = nullptr;
+            const ListLayout ll((size_t)R, tiles);
+            if (C > 0 && R > 0) {
+                // stream-ordered scratch (the reference's backward allocates its scratch too, rasterizer_impl.cu:402-430);
+                // the default pool keeps freed blocks, so steady-state calls do not reach the driver
+                static std::once_flag once;
+                std::call_once(once, [] {
+                    int dev = 0;
+                    cudaGetDevice(&dev);
+                    cudaMemPool_t pool;
+                    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                        unsigned long long keep = ~0ull;
+                        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                    }
+                });
+                cudaError_t ea = cudaMallocAsync((void**)&lists, ll.bytes, stream);
+                if (ea != cudaSuccess)
+                    return fail(F3DGS_ERR_ALLOC, w + ": cudaMallocAsync of " + std::to_string(ll.bytes) +
+                                                     " bytes for the backward instance lists failed: " +
+                                                     cudaGetErrorString(ea));
+            }
+            e = launch_composite_bwd_geom_slim(
+                vg, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix, dL_depths, dL_dmean2D, dL_dconic,
+                dL_dopacity, dL_dcolor, dL_dz, counters + 16, stream, lists ? reinterpret_cast<float*>(lists + ll.w) : nullptr,
+                lists ? reinterpret_cast<uint2*>(lists + ll.meta) : nullptr,
+                lists ? reinterpret_cast<uint32_t*>(lists + ll.cnt) : nullptr);
+            if (e == cudaSuccess && lists)
+                e = launch_feature_bwd(vp, ranges, reinterpret_cast<const float*>(lists + ll.w),
+                                       reinterpret_cast<const uint2*>(lists + ll.meta),
+                                       reinterpret_cast<const uint32_t*>(lists + ll.cnt), dL_dfeaturepix,
                                        dL_dsemantic_feature, counters + 48, stream);
+            if (lists) cudaFreeAsync(lists, stream);
         } else {
             e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,
                                      dL_dfeaturepix, dL_depths, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,

@@ -42,7 +42,7 @@ static constexpr bool kTimingB = F3DGS_TIMING_BUILD != 0;
 #define BTICK() ((kTimingB && args.dbg) ? clock64() : 0ll)
 
 #ifndef F3DGS_PAIR_SKIP
-#define F3DGS_PAIR_SKIP 0   // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
+#define F3DGS_PAIR_SKIP 1   // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
 #endif
 #ifndef F3DGS_FFMA2
 #define F3DGS_FFMA2 1   // 1: feature-gradient loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2), see composite_fwd.cu
@@ -67,29 +67,11 @@ struct BwdLayout : Layout<BPA> {
     static constexpr int kRegsFeature = BPA == 2 ? 184 : F3DGS_BWD_F1;
 };
 
-// F3DGS_BWD_HELPERS=1 (experiment): the row sums + global reductions of the parked geometric terms (`flush`, ~35 of the
-// ~175 instructions an alpha warp spends per blended instance) move to the three otherwise idle warps of the producer
-// group.  Each alpha warp's scratch becomes two buffers of kHelpSlots instances; a full buffer is handed to helper warp
-// (a mod 3) through `rfull`, which sums the rows, issues the red.global.add's and returns the buffer through `rempty`.
-#ifndef F3DGS_BWD_HELPERS
-#define F3DGS_BWD_HELPERS 0
-#endif
-#if F3DGS_BWD_HELPERS
-constexpr int kHelpSlots = kRedSlots / 2;          // instances per hand-off buffer
-constexpr int kHelpRows = kHelpSlots * kRedVals;   // rows per buffer, row = value * kHelpSlots + slot
-constexpr uint32_t kHelpDone = 0xffffffffu;        // red_n sentinel: this alpha warp has finished
-#endif
-
 template <typename RING>
 struct alignas(128) BwdSmemT {
     RING ring;
     float red[kBlocksPerTile][kRedRows][kRedStride];
     uint32_t red_gid[kBlocksPerTile][kRedSlots];
-#if F3DGS_BWD_HELPERS
-    uint32_t red_n[kBlocksPerTile][2];
-    uint64_t rfull[kBlocksPerTile][2];
-    uint64_t rempty[kBlocksPerTile][2];
-#endif
 };
 using BwdSmem = BwdSmemT<RingV2<0>>;
 
@@ -109,6 +91,10 @@ struct BwdArgs {
     float* dL_dz;        // [P]
     int vec_io;          // bit0: 128-bit loads of dL_dfeat_pix, bit1: red.v4 into dL_dfeature
     long long* dbg;      // F3DGS_TIMING=1 (timing builds only): per-warp cycle counters [cta][warp][8], else nullptr
+    // EMIT kernels (two-kernel backward): per (tile, 8x4 block) lists of the instances that blended in the block
+    float* list_w;        // [8R][32] blend weights w = alpha * T (the backward's unwound T), entry (8*range.x + b*len + i)
+    uint2* list_meta;     // [8R]     {Gaussian id, pixel mask}
+    uint32_t* list_cnt;   // [8T]     entries written per (tile, block)
 };
 
 // destination of reduced value v (0..9) of Gaussian gid: reference backward.cu:560-610 (atomicAdd targets)
@@ -125,61 +111,10 @@ __device__ __forceinline__ float* geom_dst(const BwdArgs& args, int v, uint32_t 
     }
 }
 
-#if F3DGS_BWD_HELPERS
-// Helper warp g (0..2) of the producer group: serves the hand-off buffers of alpha warps g, g+3, g+6 round-robin.
-template <int NALPHA, typename SMEM>
-__device__ __forceinline__ void helper_loop(SMEM& sm, const BwdArgs& args, int g, int lane) {
-    constexpr int kMax = 3;  // alpha warps per helper
-    uint32_t buf[kMax], phase[kMax][2];
-    bool fin[kMax];
-    int active = 0;
-#pragma unroll
-    for (int i = 0; i < kMax; i++) {
-        buf[i] = 0; phase[i][0] = phase[i][1] = 0;
-        fin[i] = (g + 3 * i) >= NALPHA;
-        active += fin[i] ? 0 : 1;
-    }
-    while (active > 0) {
-        bool progressed = false;
-#pragma unroll
-        for (int i = 0; i < kMax; i++) {
-            if (fin[i]) continue;
-            const int a = g + 3 * i;
-            const uint32_t b = buf[i];
-            if (!mbar_test(&sm.rfull[a][b], phase[i][b])) continue;
-            progressed = true;
-            phase[i][b] ^= 1;
-            buf[i] = b ^ 1;
-            const uint32_t n = sm.red_n[a][b];
-            if (n == kHelpDone) {
-                fin[i] = true;
-                active--;
-                continue;
-            }
-            for (int r = lane; r < kHelpRows; r += 32) {
-                const int slot = r % kHelpSlots, v = r / kHelpSlots;
-                if (slot < (int)n) {
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    const float4* row = reinterpret_cast<const float4*>(sm.red[a][b * kHelpRows + r]);
-#pragma unroll
-                    for (int jj = 0; jj < 8; jj++) {
-                        const float4 q = row[jj];
-                        s0 += q.x; s1 += q.y; s2 += q.z; s3 += q.w;
-                    }
-                    red_add_f1(geom_dst(args, v, sm.red_gid[a][b * kHelpSlots + slot]), (s0 + s1) + (s2 + s3));
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.rempty[a][b]);
-        }
-        if (!progressed) __nanosleep(200);
-    }
-}
-#endif
 
 // SLIM (geometric pass of the two-pass mode, CH == 0): 12 warps, ring without weight slots (106 KB of shared memory instead
 // of 175 KB), two CTAs per SM; the alpha warps keep the launch register count (80) instead of shrinking to 64.
-template <int CH, int BPA, bool SLIM = false>
+template <int CH, int BPA, bool SLIM = false, bool EMIT = false>
 __global__ void __launch_bounds__(SLIM ? (kAlphaWarp0 + Layout<BPA>::kAlphaWarps) * 32 : Layout<BPA>::kThreads, SLIM ? 2 : 1)
 composite_bwd_kernel(const BwdArgs args) {
     static_assert(!SLIM || CH == 0, "the slim layout has no feature warps");
@@ -198,25 +133,12 @@ composite_bwd_kernel(const BwdArgs args) {
 
     using L = BwdLayout<BPA>;
     ring_init<0>(ring, CH > 0 ? L::kAlphaWarps + kBlocksPerTile : L::kAlphaWarps, CH > 0);
-#if F3DGS_BWD_HELPERS
-    if (threadIdx.x == 32) {
-        for (int a = 0; a < kBlocksPerTile; a++)
-            for (int b = 0; b < 2; b++) {
-                mbar_init(&sm.rfull[a][b], 1);
-                mbar_init(&sm.rempty[a][b], 1);
-            }
-        mbar_fence_init();
-    }
-#endif
     __syncthreads();
 
     // ======================================================================== producer group
     if (warp < kAlphaWarp0) {
         reg_dec<L::kRegsProducer>();
         if (warp == kProducerWarp) producer_loop<0, true, false, RING>(ring, args.pa);
-#if F3DGS_BWD_HELPERS
-        else helper_loop<L::kAlphaWarps, SMEM>(sm, args, warp - 1, lane);
-#endif
         return;
     }
 
@@ -240,26 +162,15 @@ composite_bwd_kernel(const BwdArgs args) {
             P[bi] = Px{};
         }
         bool do_geom = false;
+        size_t ebase[BPA];      // EMIT: first list entry of this (tile, block)
+        uint32_t ecount[BPA];   // EMIT: entries written so far
+        int etile = 0;
+#pragma unroll
+        for (int bi = 0; bi < BPA; bi++) { ebase[bi] = 0; ecount[bi] = 0; }
         const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
         long long tA_full = 0, tA_wempty = 0, tA_flush = 0, nA_hits = 0, nA_pm = 0;
         const long long tA_total = BTICK();
 
-#if F3DGS_BWD_HELPERS
-        uint32_t rb = 0, ephase = 3u;           // hand-off buffer in use; bit b = parity to wait for on rempty[b] (fresh: 1)
-        bool rb_mine = false;                   // this buffer has been waited for and may be written
-        auto flush = [&]() {                    // hand the current buffer to the helper warp
-            const long long tf_ = BTICK();
-            __syncwarp();
-            if (lane == 0) {
-                sm.red_n[a][rb] = nslots;
-                mbar_arrive(&sm.rfull[a][rb]);
-            }
-            rb ^= 1;
-            nslots = 0;
-            rb_mine = false;
-            tA_flush += BTICK() - tf_;
-        };
-#else
         auto flush = [&]() {
             const long long tf_ = BTICK();
             __syncwarp();
@@ -297,7 +208,6 @@ composite_bwd_kernel(const BwdArgs args) {
             nslots = 0;
             tA_flush += BTICK() - tf_;
         };
-#endif
 
         for (;;) {
             { const long long t_ = BTICK(); mbar_wait(&ring.full[s], parity); tA_full += BTICK() - t_; }
@@ -309,6 +219,15 @@ composite_bwd_kernel(const BwdArgs args) {
                 const int tile = work / args.pa.chunks, chunk = work - tile * args.pa.chunks;
                 const int tile_x = tile % args.pa.tiles_x, tile_y = tile / args.pa.tiles_x;
                 do_geom = (chunk == 0);
+                if (EMIT) {
+                    etile = tile;
+                    const uint2 rg = args.pa.ranges[tile];
+#pragma unroll
+                    for (int bi = 0; bi < BPA; bi++) {
+                        ebase[bi] = 8 * (size_t)rg.x + (size_t)(BPA * a + bi) * (rg.y - rg.x);
+                        ecount[bi] = 0;
+                    }
+                }
 #pragma unroll
                 for (int bi = 0; bi < BPA; bi++) {
                     const int b = BPA * a + bi;
@@ -433,28 +352,18 @@ composite_bwd_kernel(const BwdArgs args) {
                                     if (lane == 0) ws->pm[k] = pm;
                                     km |= 1u << k;
                                 }
+                                if (EMIT) {  // one 128-byte row of weights + {id, mask} per blended (block, instance)
+                                    const size_t e = ebase[bi] + ecount[bi];
+                                    args.list_w[e * 32 + lane] = wgt;
+                                    if (lane == 0) args.list_meta[e] = make_uint2(st.gid[k], pm);
+                                    ecount[bi]++;
+                                }
                                 if (do_geom) {
-#if F3DGS_BWD_HELPERS
-                                    if (!rb_mine) {  // first instance parked into this buffer: the helper must be done with it
-                                        const long long tf_ = BTICK();
-                                        mbar_wait(&sm.rempty[a][rb], (ephase >> rb) & 1u);
-                                        ephase ^= 1u << rb;
-                                        rb_mine = true;
-                                        tA_flush += BTICK() - tf_;
-                                    }
-#pragma unroll
-                                    for (int i = 0; i < kRedVals; i++)
-                                        red[rb * kHelpRows + i * kHelpSlots + nslots][lane] = v[i];
-                                    if (lane == 0) red_gid[rb * kHelpSlots + nslots] = st.gid[k];
-                                    nslots++;
-                                    if (nslots == kHelpSlots) flush();
-#else
 #pragma unroll
                                     for (int i = 0; i < kRedVals; i++) red[i * kRedSlots + nslots][lane] = v[i];
                                     if (lane == 0) red_gid[nslots] = st.gid[k];
                                     nslots++;
                                     if (nslots == kRedSlots) flush();
-#endif
                                 }
                             }
                         }
@@ -473,19 +382,14 @@ composite_bwd_kernel(const BwdArgs args) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[s]);
+            if (EMIT && last && lane == 0) {
+#pragma unroll
+                for (int bi = 0; bi < BPA; bi++) args.list_cnt[(size_t)etile * kBlocksPerTile + BPA * a + bi] = ecount[bi];
+            }
             if (last && nslots > 0) flush();
             if (++s == kStages) { s = 0; parity ^= 1; }
             if (CH > 0 && ++j == kWSlots) { j = 0; wparity ^= 1; }
         }
-#if F3DGS_BWD_HELPERS
-        // every batch was handed over at the end of its tile; tell the helper that this alpha warp is finished
-        if (!rb_mine) mbar_wait(&sm.rempty[a][rb], (ephase >> rb) & 1u);
-        __syncwarp();
-        if (lane == 0) {
-            sm.red_n[a][rb] = kHelpDone;
-            mbar_arrive(&sm.rfull[a][rb]);
-        }
-#endif
         if (kTimingB && args.dbg && lane == 0) {
             long long* d = args.dbg + (blockIdx.x * 32 + warp) * 8;
             d[0] = clock64() - tA_total; d[1] = tA_full; d[2] = tA_wempty; d[3] = tA_flush; d[4] = nA_hits; d[5] = nA_pm;
@@ -736,8 +640,10 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
                                            const SplatRec* rec, const float* bg, const float* final_T,
                                            const uint32_t* n_contrib, const float* dL_dpix, const float* dL_ddepth,
                                            float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-                                           float* dL_dz, int* work_counter, cudaStream_t s) {
+                                           float* dL_dz, int* work_counter, cudaStream_t s, float* list_w,
+                                           uint2* list_meta, uint32_t* list_cnt) {
     using SMEM = BwdSmemT<RingSlim>;
+    const bool emit = list_w != nullptr;
     const size_t smem = sizeof(SMEM);
     static int sms_of_device[64] = {0};
     int dev = 0;
@@ -746,6 +652,9 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
     if (sms_of_device[dev] == 0) {
         cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(composite_bwd_kernel<0, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem);
         if (e != cudaSuccess) return e;
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -759,10 +668,14 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
     a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib; a.dL_dpix = dL_dpix; a.dL_dfeat_pix = nullptr;
     a.dL_ddepth = dL_ddepth; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
     a.dL_dcolor = dL_dcolor; a.dL_dfeature = nullptr; a.dL_dz = dL_dz; a.vec_io = 0; a.dbg = nullptr;
+    a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int grid = min(a.pa.num_tiles, 2 * sms_of_device[dev]);
-    composite_bwd_kernel<0, 1, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
+    if (emit)
+        composite_bwd_kernel<0, 1, true, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
+    else
+        composite_bwd_kernel<0, 1, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
     g_launches++;
     return cudaGetLastError();
 }
@@ -785,6 +698,7 @@ cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, cons
     a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib; a.dL_dpix = dL_dpix; a.dL_dfeat_pix = dL_dfeat_pix;
     a.dL_ddepth = dL_ddepth; a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
     a.dL_dcolor = dL_dcolor; a.dL_dfeature = dL_dfeature; a.dL_dz = dL_dz; a.vec_io = 0; a.dbg = nullptr;
+    a.list_w = nullptr; a.list_meta = nullptr; a.list_cnt = nullptr;
     if (vp.C == 0) return F3DGS_BWD_DISPATCH(0);
     if (vp.C <= 32) return F3DGS_BWD_DISPATCH(32);
     if (vp.C <= 64) return F3DGS_BWD_DISPATCH(64);

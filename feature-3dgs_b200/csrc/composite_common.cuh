@@ -116,7 +116,7 @@ struct alignas(128) RingSlim {
 };
 
 #ifndef F3DGS_EXACT_CULL
-#define F3DGS_EXACT_CULL 0   // 1: exact ellipse-vs-rectangle footprint test after the bounding-box test (see below)
+#define F3DGS_EXACT_CULL 1   // 1: exact ellipse-vs-rectangle footprint test after the bounding-box test (see below); 0: box only
 #endif
 
 // Can the region where alpha >= 1/255 reach the pixel rectangle [x0,x1] x [y0,y1] (pixel-centre coordinates)?

@@ -41,7 +41,7 @@ namespace f3dgs {
 #define F3DGS_DIAG_NO_FMA 0    // diagnostic builds only (WRONG RESULTS): feature warps consume their slots without the FMAs
 #endif
 #ifndef F3DGS_PAIR_SKIP
-#define F3DGS_PAIR_SKIP 0      // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
+#define F3DGS_PAIR_SKIP 1      // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
 #endif
 #ifndef F3DGS_FEAT_PREFETCH
 #define F3DGS_FEAT_PREFETCH 0  // 1: software-pipeline the sparse feature loop by one instance (mask + feature float4)
@@ -59,10 +59,6 @@ struct FwdArgs {
     float* out_depth;
     int vec_store;
     long long* dbg;  // F3DGS_TIMING=1: per-warp cycle counters [cta][warp][8], else nullptr
-    // two-pass mode (EMIT kernels only, see composite_split.cu): per (tile, 8x4 block) lists of the blended instances
-    float* list_w;        // [8R][32] blend weights of the block's pixels, entry (8*range.x + b*len + i)
-    uint2* list_meta;     // [8R]     {Gaussian id, pixel mask}
-    uint32_t* list_cnt;   // [8T]     entries written per (tile, block)
 };
 
 // Forward register budget.  BPA == 1 (20 warps, launched at 96 regs/thread = 61440 in the CTA pool):
@@ -76,14 +72,11 @@ struct FwdLayout : Layout<BPA> {
     static constexpr bool kPrefetchW = BPA == 2 || F3DGS_FWD_F1 >= 168;
 };
 
-// SLIM (two-pass alpha pass only, CH == 0): no feature warps are launched (12 warps), the ring has no weight slots and two
-// CTAs share an SM (launch bound 384 x 2 -> 80 registers; the alpha warps keep them instead of shrinking to 64).
-template <int CH, int BPA, bool EMIT = false, bool SLIM = false>
-__global__ void __launch_bounds__(SLIM ? (kAlphaWarp0 + Layout<BPA>::kAlphaWarps) * 32 : Layout<BPA>::kThreads, SLIM ? 2 : 1)
+template <int CH, int BPA>
+__global__ void __launch_bounds__(Layout<BPA>::kThreads, 1)
 composite_fwd_kernel(const FwdArgs args) {
-    static_assert(!SLIM || CH == 0, "the slim layout has no feature warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using RING = typename RingSelect<CH, SLIM>::type;
+    using RING = RingV2<CH>;
     RING& ring = *reinterpret_cast<RING*>(smem_raw);
     // The warp index goes through a shuffle so that ptxas knows it is warp-uniform: role branches, ring/slot addresses
     // and everything loaded from them (instance masks, work ids) then live in uniform registers, the per-quad branches
@@ -113,15 +106,12 @@ composite_fwd_kernel(const FwdArgs args) {
 
     // ======================================================================== alpha warps
     if (warp < L::kFeatWarp0) {
-        if (!SLIM) reg_dec<L::kRegsAlpha>();
+        reg_dec<L::kRegsAlpha>();
         const int a = warp - kAlphaWarp0;  // owns blocks BPA*a .. BPA*a + BPA-1
         int s = 0, j = 0;
         uint32_t parity = 0, wparity = 1;  // wempty: fresh barrier falls through on parity 1
         float T[BPA], Cr[BPA], Cg[BPA], Cb[BPA], Dp[BPA], pxf[BPA], pyf[BPA], fbx0[BPA], fby0[BPA];
         uint32_t last_contrib[BPA];
-        size_t ebase[BPA];      // EMIT: first list entry of this (tile, block)
-        uint32_t ecount[BPA];   // EMIT: entries written so far
-        int etile = 0;
         int px[BPA], py[BPA], chunk = 0;
         bool done[BPA], inside[BPA], blk_done[BPA];
 #pragma unroll
@@ -141,15 +131,6 @@ composite_fwd_kernel(const FwdArgs args) {
                 const int tile = work / args.pa.chunks;
                 chunk = work - tile * args.pa.chunks;
                 const int tile_x = tile % args.pa.tiles_x, tile_y = tile / args.pa.tiles_x;
-                if (EMIT) {
-                    etile = tile;
-                    const uint2 rg = args.pa.ranges[tile];
-#pragma unroll
-                    for (int bi = 0; bi < BPA; bi++) {
-                        ebase[bi] = 8 * (size_t)rg.x + (size_t)(BPA * a + bi) * (rg.y - rg.x);
-                        ecount[bi] = 0;
-                    }
-                }
 #pragma unroll
                 for (int bi = 0; bi < BPA; bi++) {
                     const int b = BPA * a + bi;
@@ -352,12 +333,6 @@ composite_fwd_kernel(const FwdArgs args) {
                                 if (lane == 0) ws->pm[kk[u]] = pm;
                                 km |= (pm ? 1u : 0u) << kk[u];
                             }
-                            if (EMIT && pm) {  // warp-uniform: one 128-byte row of weights + {id, mask} per blended instance
-                                const size_t e = ebase[bi] + ecount[bi];
-                                args.list_w[e * 32 + lane] = wgt;
-                                if (lane == 0) args.list_meta[e] = make_uint2(st.gid[kk[u]], pm);
-                                ecount[bi]++;
-                            }
                         }
                     }
                     if (__all_sync(0xffffffffu, done[bi])) {
@@ -379,10 +354,6 @@ composite_fwd_kernel(const FwdArgs args) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[s]);
-            if (EMIT && last && lane == 0) {
-#pragma unroll
-                for (int bi = 0; bi < BPA; bi++) args.list_cnt[(size_t)etile * kBlocksPerTile + BPA * a + bi] = ecount[bi];
-            }
             if (last && chunk == 0) {
 #pragma unroll
                 for (int bi = 0; bi < BPA; bi++)
@@ -667,7 +638,6 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     a.pa.use_bulk = (CH > 0 && vp.C % 4 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0) ? 1 : 0;
     a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib;
     a.out_color = out_color; a.out_feature = out_feature; a.out_depth = out_depth;
-    a.list_w = nullptr; a.list_meta = nullptr; a.list_cnt = nullptr;
     a.vec_store = (vp.W % 4 == 0 && (reinterpret_cast<uintptr_t>(out_feature) & 15) == 0) ? 1 : 0;
     if (vp.W % 8 == 0 && (reinterpret_cast<uintptr_t>(out_feature) & 31) == 0) a.vec_store |= 2;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
@@ -695,76 +665,6 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
                 CH, BPA, prod / grid, A[0] / (grid * nA), A[1] / (grid * nA), A[2] / (grid * nA), A[3] / (grid * nA), A[4] / (grid * nA),
                 F[0] / (grid * 8), F[1] / (grid * 8), F[2] / (grid * 8), F[3] / (grid * 8), F[4] / (grid * 8));
     }
-    return cudaGetLastError();
-}
-
-// Alpha pass of the two-pass mode: the C = 0 kernel (no feature warps at work) that also writes the per-block instance lists.
-cudaError_t launch_composite_fwd_emit(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
-                                      const SplatRec* rec, const float* bg, float* final_T, uint32_t* n_contrib,
-                                      float* out_color, float* out_depth, float* list_w, uint2* list_meta,
-                                      uint32_t* list_cnt, int* work_counter, cudaStream_t s) {
-    const size_t smem = sizeof(RingV2<0>);
-    static int sms_of_device[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (sms_of_device[dev] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
-        int n = 0;
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms_of_device[dev] = n > 0 ? n : 148;
-    }
-    FwdArgs a;
-    a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec;
-    a.pa.features = nullptr; a.pa.n_contrib = nullptr; a.pa.work_counter = work_counter;
-    a.pa.W = vp.W; a.pa.H = vp.H; a.pa.C = 0;
-    a.pa.tiles_x = (int)vp.grid_x; a.pa.num_tiles = (int)(vp.grid_x * vp.grid_y); a.pa.chunks = 1; a.pa.use_bulk = 0;
-    a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib;
-    a.out_color = out_color; a.out_feature = nullptr; a.out_depth = out_depth;
-    a.vec_store = 0; a.dbg = nullptr;
-    a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
-    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
-    if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles, sms_of_device[dev]);
-    composite_fwd_kernel<0, 1, true><<<grid, Layout<1>::kThreads, smem, s>>>(a);
-    g_launches++;
-    return cudaGetLastError();
-}
-
-// Same alpha pass with the slim layout: 12 warps per CTA, two CTAs per SM (F3DGS_SPLIT=2).
-cudaError_t launch_composite_fwd_emit_slim(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
-                                           const SplatRec* rec, const float* bg, float* final_T, uint32_t* n_contrib,
-                                           float* out_color, float* out_depth, float* list_w, uint2* list_meta,
-                                           uint32_t* list_cnt, int* work_counter, cudaStream_t s) {
-    const size_t smem = sizeof(RingSlim);
-    static int sms_of_device[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (sms_of_device[dev] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<0, 1, true, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int n = 0;
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms_of_device[dev] = n > 0 ? n : 148;
-    }
-    FwdArgs a;
-    a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec;
-    a.pa.features = nullptr; a.pa.n_contrib = nullptr; a.pa.work_counter = work_counter;
-    a.pa.W = vp.W; a.pa.H = vp.H; a.pa.C = 0;
-    a.pa.tiles_x = (int)vp.grid_x; a.pa.num_tiles = (int)(vp.grid_x * vp.grid_y); a.pa.chunks = 1; a.pa.use_bulk = 0;
-    a.bg = bg; a.final_T = final_T; a.n_contrib = n_contrib;
-    a.out_color = out_color; a.out_feature = nullptr; a.out_depth = out_depth;
-    a.vec_store = 0; a.dbg = nullptr;
-    a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
-    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
-    if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles, 2 * sms_of_device[dev]);
-    composite_fwd_kernel<0, 1, true, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
-    g_launches++;
     return cudaGetLastError();
 }
 

@@ -211,11 +211,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
                 if (!blk_done && n > 0) {
                     const int e0 = h * kKS;
                     bool hit = false;
-                    if (lane < kKS && e0 + lane < (int)n) {
-                        const float4 r0 = st.rec0[e0 + lane];
-                        hit = (r0.x + r0.z >= fbx0) && (r0.x - r0.z <= fbx0 + 7.f) && (r0.y + r0.w >= fby0) &&
-                              (r0.y - r0.w <= fby0 + 3.f);
-                    }
+                    if (lane < kKS && e0 + lane < (int)n)
+                        hit = footprint_hits_rect(st.rec0[e0 + lane], st.rec1[e0 + lane], fbx0, fbx0 + 7.f, fby0, fby0 + 3.f);
                     uint32_t am = __ballot_sync(0xffffffffu, hit);
                     while (am) {
                         // up to 4 instances per trip, branch-free alpha evaluation (see composite_fwd.cu)

@@ -59,27 +59,16 @@ cudaError_t launch_composite_fwd_tc(const ViewParams& vp, const uint2* ranges, c
                                     float* final_T, uint32_t* n_contrib, float* out_color,
                                     float* out_feature, float* out_depth, int* work_counter, cudaStream_t s);
 
-// alpha pass of the two-pass mode (composite_split.cu): the C = 0 forward that also writes the per-block instance lists
-cudaError_t launch_composite_fwd_emit(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
-                                      const SplatRec* rec, const float* bg, float* final_T, uint32_t* n_contrib,
-                                      float* out_color, float* out_depth, float* list_w, uint2* list_meta,
-                                      uint32_t* list_cnt, int* work_counter, cudaStream_t s);
-
-cudaError_t launch_composite_fwd_emit_slim(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
-                                           const SplatRec* rec, const float* bg, float* final_T, uint32_t* n_contrib,
-                                           float* out_color, float* out_depth, float* list_w, uint2* list_meta,
-                                           uint32_t* list_cnt, int* work_counter, cudaStream_t s);
-// geometric-gradient pass of the two-pass mode with the slim layout (composite_bwd.cu)
+// geometric-gradient kernel of the two-kernel backward (composite_bwd.cu): alpha-only, two CTAs per SM; with list pointers it
+// also emits the per-(tile, block) blend weights for launch_feature_bwd
 cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                            const SplatRec* rec, const float* bg, const float* final_T,
                                            const uint32_t* n_contrib, const float* dL_dpix, const float* dL_ddepth,
                                            float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-                                           float* dL_dz, int* work_counter, cudaStream_t s);
+                                           float* dL_dz, int* work_counter, cudaStream_t s, float* list_w = nullptr,
+                                           uint2* list_meta = nullptr, uint32_t* list_cnt = nullptr);
 
-// ---- composite_split.cu (two-pass mode, opt-in)
-cudaError_t launch_feature_fwd(const ViewParams& vp, const uint2* ranges, const float* list_w, const uint2* list_meta,
-                               const uint32_t* list_cnt, const float* features, float* out_feature, int* work_counter,
-                               cudaStream_t s);
+// ---- feature_bwd.cu: feature gradient from the instance lists (second kernel of the two-kernel backward)
 cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const float* list_w, const uint2* list_meta,
                                const uint32_t* list_cnt, const float* dL_dfeat_pix, float* dL_dfeature,
                                int* work_counter, cudaStream_t s);

@@ -5,7 +5,7 @@ binding -> C ABI, against
 on identical seeded inputs.  Bars (BASELINE.json north_star): bit-exact tile/key indexing (radii,
 num_rendered, point_list, ranges, n_contrib); RGB/feature/depth/gradients within 1e-4 relative
 (parity.RTOL + ATOL_REL floor).  On top of the bar, colour / depth / final_T are asserted BIT-identical to
-the reference build (same fp32 operation sequence), the feature map to 2e-6 of its scale.
+the reference build (same fp32 operation sequence), the feature map to 5e-6 of its scale.
 Nothing here reads /root/reference.
 """
 import copy
@@ -37,7 +37,9 @@ def _check(sc, cam, with_grads=True, vs_ref=True, vs_oracle=True, exact_vs_ref=T
             for k in ("color", "depth", "final_T"):
                 assert np.array_equal(ours[k], ref[k]), f"{k} not bit-identical to the reference build"
             if sc.C:
-                assert rep["feature_map"]["max_abs_err"] <= 2e-6 * max(rep["feature_map"]["scale"], 1e-6)
+                # fp32-pipe kernel: <= 2e-6 of scale; tensor-core path (C > 64, compensated 3xTF32): <= 5e-6 of scale.
+                # Both are ~20-50x inside the 1e-4 bar checked by parity.compare above.
+                assert rep["feature_map"]["max_abs_err"] <= 5e-6 * max(rep["feature_map"]["scale"], 1e-6)
         n += 1
     if vs_oracle:
         okw = {k: v for k, v in kw.items() if k in ("colors_precomp", "cov3D_precomp")}

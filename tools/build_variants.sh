@@ -10,6 +10,6 @@ while [ $# -ge 2 ]; do
   n=$1; f=$2; shift 2
   d=feature-3dgs_b200/variants/$n; mkdir -p $d
   ( nvcc -c $S/composite_fwd.cu -o $d/fwd.o $FL $f > $d/fwd.log 2>&1 & nvcc -c $S/composite_bwd.cu -o $d/bwd.o $FL $f > $d/bwd.log 2>&1 & wait )
-  nvcc -shared -o $d/libf3dgs_b200.so $B/api.cu.o $B/binning.cu.o $B/preprocess.cu.o $B/composite_split.cu.o $d/fwd.o $d/bwd.o -gencode arch=compute_100a,code=sm_100a -cudart static
+  nvcc -shared -o $d/libf3dgs_b200.so $B/api.cu.o $B/binning.cu.o $B/preprocess.cu.o $B/feature_bwd.cu.o $d/fwd.o $d/bwd.o -gencode arch=compute_100a,code=sm_100a -cudart static
   echo "built $n ($f)"; grep -h "error" $d/*.log || true
 done

@@ -129,14 +129,13 @@ def main():
         os.environ.pop("F3DGS_TC", None)
         if name.endswith("+tc"):
             os.environ["F3DGS_TC"] = "1"  # tensor-core feature contraction (read once per library instance)
-        if name.endswith("+notc"):
+        if "+notc" in name:
             os.environ["F3DGS_TC"] = "0"
+        os.environ.pop("F3DGS_BWD2", None)
+        if "+bwd1" in name:
+            os.environ["F3DGS_BWD2"] = "0"  # fused single-kernel backward
         if name.startswith("timing"):
             os.environ["F3DGS_TIMING"] = "1"
-        if name.endswith("+split"):
-            os.environ["F3DGS_SPLIT"] = "1"  # read once per library instance at its first forward
-        if name.endswith("+split2"):
-            os.environ["F3DGS_SPLIT"] = "2"
         v = Variant(name)
         out = dict(color=torch.empty(3, H, W, device=dev), feature=torch.empty(max(C, 1), H, W, device=dev),
                    depth=torch.empty(1, H, W, device=dev), radii=torch.empty(P, dtype=torch.int32, device=dev))
