@@ -98,6 +98,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// Wait with a real sleep between polls, for roles that are far ahead of / behind their partner (epilogue waiting for a whole
+// tile, producer waiting for a free stage, ...).  The poll loop of mbar_wait costs three issue slots every ~20 cycles per
+// waiting warp: with ten waiting warps per SM that was 43% of all instructions executed by the tensor-core forward kernel
+// (ncu source counters, profiles/r02_*), taken from the warps on the critical path.  `ns` bounds the added wake-up latency.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "F3DGS_SWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra F3DGS_SDONE_%=;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra F3DGS_SWAIT_%=;\n\t"
+        "F3DGS_SDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
 // non-blocking probe of a phase (helper warps that serve several barriers round-robin)
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

@@ -48,7 +48,14 @@ static constexpr bool kTimingB = F3DGS_TIMING_BUILD != 0;
 #define F3DGS_FFMA2 1   // 1: feature-gradient loop on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2), see composite_fwd.cu
 #endif
 
-constexpr int kRedSlots = 8;
+#ifndef F3DGS_RED_SLOTS
+#define F3DGS_RED_SLOTS 8
+#endif
+#ifndef F3DGS_SLIM_CTAS
+#define F3DGS_SLIM_CTAS 2   // CTAs per SM of the alpha-only (SLIM) layout
+#endif
+constexpr int kRedSlots = F3DGS_RED_SLOTS;
+constexpr int kSlimCtas = F3DGS_SLIM_CTAS;
 constexpr int kRedVals = 10;
 constexpr int kRedRows = kRedSlots * kRedVals;
 constexpr int kRedStride = 36;  // floats per row: lanes park at [row][lane] (conflict-free), rows are summed with
@@ -115,7 +122,7 @@ __device__ __forceinline__ float* geom_dst(const BwdArgs& args, int v, uint32_t 
 // SLIM (geometric pass of the two-pass mode, CH == 0): 12 warps, ring without weight slots (106 KB of shared memory instead
 // of 175 KB), two CTAs per SM; the alpha warps keep the launch register count (80) instead of shrinking to 64.
 template <int CH, int BPA, bool SLIM = false, bool EMIT = false>
-__global__ void __launch_bounds__(SLIM ? (kAlphaWarp0 + Layout<BPA>::kAlphaWarps) * 32 : Layout<BPA>::kThreads, SLIM ? 2 : 1)
+__global__ void __launch_bounds__(SLIM ? (kAlphaWarp0 + Layout<BPA>::kAlphaWarps) * 32 : Layout<BPA>::kThreads, SLIM ? kSlimCtas : 1)
 composite_bwd_kernel(const BwdArgs args) {
     static_assert(!SLIM || CH == 0, "the slim layout has no feature warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -671,7 +678,7 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
     a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles, 2 * sms_of_device[dev]);
+    const int grid = min(a.pa.num_tiles, kSlimCtas * sms_of_device[dev]);
     if (emit)
         composite_bwd_kernel<0, 1, true, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
     else

@@ -65,7 +65,7 @@ constexpr int kDoneSlots = 8;       // > kStages: the producer is never further 
 
 template <int CH>
 struct alignas(128) Stage {
-    float feat[kStageEntries][CH > 0 ? CH : 4];  // CH == 0: 512 B dummy, never touched
+    float feat[CH > 0 ? kStageEntries : 1][CH > 0 ? CH : 4];  // CH == 0: 16 B dummy, never touched
     float4 rec0[kStageEntries];                   // x, y, ex, ey
     float4 rec1[kStageEntries];                   // conic a, b, c, opacity
     float4 rec2[kStageEntries];                   // r, g, b, depth
@@ -155,6 +155,18 @@ __device__ __forceinline__ bool footprint_hits_rect(const float4 r0, const float
     return box;
 #endif
 }
+
+// Record ring only (tensor-core kernels: no weight slots at all, the weights go into the MMA operand stages).
+struct alignas(128) RingRec {
+    static constexpr int kWB = 0, kWJ = 0;
+    Stage<0> stage[kStages];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t listed[kStages];
+    uint64_t wfull[1][1];   // never initialised or used (kWB == 0); keeps ring_init<> well-formed
+    uint64_t wempty[1][1];
+    uint32_t done_mask[kDoneSlots];
+};
 
 template <int CH, bool SLIM>
 struct RingSelect {
@@ -256,7 +268,7 @@ __device__ __forceinline__ void producer_loop(RING& ring, const ProducerArgs& pa
             s = 0;
             empty_parity ^= 1;
         }
-        mbar_wait(&ring.empty[s], empty_parity);
+        mbar_wait_sleep(&ring.empty[s], empty_parity, 64);  // the producer runs stages ahead: sleep, do not spin
     };
 
     const int num_work = pa.num_tiles * pa.chunks;

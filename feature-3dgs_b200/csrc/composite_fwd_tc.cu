@@ -20,20 +20,49 @@
 //   epilogue warps (4)    tcgen05.ld: lane = channel, 32 columns = the 32 pixels of one block -> four 256-bit stores per
 //                         block into the channel's CHW plane (full 32-byte sectors).
 // Channel counts above 128 run as extra work items (chunks of 128 channels), as in composite_fwd.cu.
+#include <cstdio>
+#include <cstdlib>
+
 #include "composite_common.cuh"
 #include "tc_common.cuh"
+
+#ifndef F3DGS_TIMING_BUILD
+#define F3DGS_TIMING_BUILD 0   // 1 (tools/build_variants.sh "timing"): per-role cycle counters, printed when F3DGS_TIMING is set
+#endif
 
 namespace f3dgs {
 
 namespace {
 
-constexpr int kKS = 16;         // instances per operand stage (two K=8 MMA steps)
-constexpr int kOpStages = 4;    // operand ring depth
+// Two configurations (NCTA = CTAs per SM).  The kernel is bound by the alpha warps' dependent chains (8 warps per CTA), so
+// the default is TWO CTAs per SM: 16 alpha warps per SM hide each other's latencies; each CTA then owns half of the
+// tensor memory (one accumulator buffer: its epilogue overlaps the other CTA's MMAs) and half of the shared memory.
+//   NCTA = 1: 20 warps (producer, MMA, 2 idle, 8 alpha, 4 convert, 4 epilogue), 4 operand stages, two accumulator buffers
+//   NCTA = 2: 16 warps (producer, MMA, 2 convert, 8 alpha, 4 epilogue),         2 operand stages, one accumulator buffer
+#ifndef F3DGS_TC_CTAS
+#define F3DGS_TC_CTAS 1
+#endif
+constexpr int kNCta = F3DGS_TC_CTAS;
+constexpr int kKS = 16;                          // instances per operand stage (two K=8 MMA steps)
+constexpr int kOpStages = kNCta == 1 ? 4 : 2;    // operand ring depth
+constexpr int kAccBufs = kNCta == 1 ? 2 : 1;     // accumulator buffers of 256 columns
+constexpr int kTmemCols = 256 * kAccBufs;
 constexpr int kMmaWarp = 1;
 constexpr int kAlpha0 = 4, kAlphaN = 8;
-constexpr int kConv0 = 12, kConvN = 4;
-constexpr int kEpi0 = 16, kEpiN = 4;   // kEpi0 % 4 == 0: epilogue warp e reads TMEM lanes 32e .. 32e+31
+constexpr int kConv0 = kNCta == 1 ? 12 : 2, kConvN = kNCta == 1 ? 4 : 2;
+constexpr int kEpi0 = kNCta == 1 ? 16 : 12, kEpiN = 4;   // kEpi0 % 4 == 0: epilogue warp e reads TMEM lanes 32e .. 32e+31
 constexpr int kThreadsTc = (kEpi0 + kEpiN) * 32;
+#ifndef F3DGS_TC_CONV_BATCH
+#define F3DGS_TC_CONV_BATCH (F3DGS_TC_CTAS == 1 ? 16 : 8)
+#endif
+constexpr int kConvBatch = F3DGS_TC_CONV_BATCH;  // feature rows a convert warp keeps in flight
+// diagnostic builds only (WRONG RESULTS): drop one role's work to see what bounds the kernel (tools/build_variants.sh)
+#ifndef F3DGS_TC_DIAG
+#define F3DGS_TC_DIAG 0   // 1: no MMAs, 2: alpha warps skip the evaluation, 4: no zero fill of the weight rows, 8: no feature loads
+#endif
+#ifndef F3DGS_TC_BLOCK_EXACT
+#define F3DGS_TC_BLOCK_EXACT 0   // 1: exact ellipse test at block level too (the producer's tile-level test follows F3DGS_EXACT_CULL)
+#endif
 
 struct alignas(1024) OpStage {
     float Fhi[4][kKS][32];   // A operand: [channel block][instance][32 channels]
@@ -45,14 +74,16 @@ static_assert(sizeof(OpStage) == 48 * 1024, "operand stage is 48 KB");
 
 struct alignas(1024) TcSmem {
     OpStage op[kOpStages];
-    RingSlim ring;                       // record ring (composite_common.cuh)
+    RingRec ring;                        // record ring (composite_common.cuh)
     uint64_t op_full[kOpStages];         // 8 alpha warps + 1 convert warp have written the stage
     uint64_t op_empty[kOpStages];        // the stage's MMAs have completed (tcgen05.commit)
-    uint64_t tmem_full[2];               // a tile's accumulators are complete
-    uint64_t tmem_empty[2];              // the epilogue has read them
-    int32_t tile_work[2];
+    uint64_t tmem_full[kAccBufs];        // a tile's accumulators are complete
+    uint64_t tmem_empty[kAccBufs];       // the epilogue has read them
+    int32_t tile_work[kAccBufs];
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(TcSmem) + 1024 <= (kNCta == 1 ? 227 * 1024 : 112 * 1024), "shared memory budget per CTA");
 
 struct FwdTcArgs {
     ProducerArgs pa;
@@ -64,13 +95,25 @@ struct FwdTcArgs {
     float* out_feature;
     float* out_depth;
     int vec_store;  // bit1: 256-bit stores legal (W % 8 == 0, 32-byte aligned planes)
+    long long* dbg;  // timing builds only: [cta][warp][8] cycle counters, else nullptr
 };
+constexpr bool kTimingTc = F3DGS_TIMING_BUILD != 0;
+#define TTICK() ((kTimingTc && args.dbg) ? clock64() : 0ll)
+#define TWAIT(acc, bar, par) do { const long long t_ = TTICK(); mbar_wait(bar, par); acc += TTICK() - t_; } while (0)
+#define TWAITS(acc, bar, par, ns) do { const long long t_ = TTICK(); mbar_wait_sleep(bar, par, ns); acc += TTICK() - t_; } while (0)
+#define TDUMP(a0, a1, a2, a3, a4, a5)                                                                   \
+    do {                                                                                                \
+        if (kTimingTc && args.dbg && lane == 0) {                                                       \
+            long long* d_ = args.dbg + ((size_t)blockIdx.x * 32 + warp) * 8;                            \
+            d_[0] = (a0); d_[1] = (a1); d_[2] = (a2); d_[3] = (a3); d_[4] = (a4); d_[5] = (a5);         \
+        }                                                                                               \
+    } while (0)
 
-__global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const FwdTcArgs args) {
+__global__ void __launch_bounds__(kThreadsTc, kNCta) composite_fwd_tc_kernel(const FwdTcArgs args) {
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B atoms need 1024-byte alignment: align by hand (the launcher asks for 1 KB of slack)
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u));
-    RingSlim& ring = sm.ring;
+    RingRec& ring = sm.ring;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int W = args.pa.W, H = args.pa.H, C = args.pa.C;
@@ -82,7 +125,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             mbar_init(&sm.op_full[i], kAlphaN + 1);
             mbar_init(&sm.op_empty[i], 1);
         }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kAccBufs; i++) {
             mbar_init(&sm.tmem_full[i], 1);
             mbar_init(&sm.tmem_empty[i], kEpiN);
         }
@@ -94,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_async_smem();
     }
-    if (warp == kMmaWarp) tmem_alloc_512(&sm.tmem_base);
+    if (warp == kMmaWarp) tmem_alloc<kTmemCols>(&sm.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -102,23 +145,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
 
     if (warp == kProducerWarp) {
         // ==================================================================== producer
-        producer_loop<0, false, false, RingSlim>(ring, args.pa);
+        const long long t_tot = TTICK();
+        producer_loop<0, false, false, RingRec>(ring, args.pa);
+        TDUMP(TTICK() - t_tot, 0, 0, 0, 0, 0);
     } else if (warp == kMmaWarp) {
         // ==================================================================== MMA issuer
         constexpr uint32_t kIdesc = umma_idesc_tf32(128, 256, 1, 1);
         int s = 0, os = 0, buf = 0;
         uint32_t parity = 0, op_round = 0, tile_seq = 0;
         bool fresh = true;
+        long long t_tot = TTICK(), w_full = 0, w_tmem = 0, w_op = 0, n_st = 0;
         for (;;) {
-            mbar_wait(&ring.full[s], parity);
+            TWAIT(w_full, &ring.full[s], parity);
             const Stage<0>& st = ring.stage[s];
             const uint32_t n = st.n, last = st.last, first = st.first;
             const int work = st.work;
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[s]);
             if (first || work < 0) {
-                buf = (int)(tile_seq & 1u);
-                mbar_wait(&sm.tmem_empty[buf], ((tile_seq >> 1) & 1u) ^ 1u);
+                buf = (int)(tile_seq % kAccBufs);
+                TWAITS(w_tmem, &sm.tmem_empty[buf], ((tile_seq / kAccBufs) & 1u) ^ 1u, 64);
                 if (lane == 0) {
                     sm.tile_work[buf] = work;
                     __threadfence_block();
@@ -135,7 +181,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             for (int h = 0; h < nh; h++) {
                 const int cnt = max(0, min(kKS, (int)n - h * kKS));
                 const int ksteps = cnt > 8 ? 2 : 1;
-                mbar_wait(&sm.op_full[os], op_round & 1u);
+                TWAITS(w_op, &sm.op_full[os], op_round & 1u, 32);
+                n_st++;
                 tc_fence_after();
                 if (lane == 0) {
                     const OpStage& op = sm.op[os];
@@ -149,9 +196,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
                         const uint64_t a_lo = umma_desc(fl + g * 1024, kKS * 128, 512, kUmmaSw128Base32);
                         const uint64_t b_hi = umma_desc(wh + g * 1024, kKS * 128, 512, kUmmaSw128Base32);
                         const uint64_t b_lo = umma_desc(wl + g * 1024, kKS * 128, 512, kUmmaSw128Base32);
-                        umma_tf32_ss(d, a_hi, b_hi, kIdesc, (fresh && g == 0) ? 0u : 1u);
-                        umma_tf32_ss(d, a_hi, b_lo, kIdesc, 1u);
-                        umma_tf32_ss(d, a_lo, b_hi, kIdesc, 1u);
+                        if (!(F3DGS_TC_DIAG & 1)) {
+                            umma_tf32_ss(d, a_hi, b_hi, kIdesc, (fresh && g == 0) ? 0u : 1u);
+                            umma_tf32_ss(d, a_hi, b_lo, kIdesc, 1u);
+                            umma_tf32_ss(d, a_lo, b_hi, kIdesc, 1u);
+                        }
                     }
                     umma_commit(&sm.op_empty[os]);
                     if (last && h == nh - 1) umma_commit(&sm.tmem_full[buf]);
@@ -162,6 +211,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             }
             if (++s == kStages) { s = 0; parity ^= 1; }
         }
+        TDUMP(TTICK() - t_tot, w_full, w_tmem, w_op, n_st, 0);
     } else if (warp >= kAlpha0 && warp < kAlpha0 + kAlphaN) {
         // ==================================================================== alpha warps
         const int b = warp - kAlpha0;  // 8x4 pixel block of the tile; lane = pixel, row-major inside the block
@@ -172,8 +222,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
         uint32_t last_contrib = 0;
         int px = 0, py = 0;
         bool done = true, inside = false, blk_done = true;
+        long long t_tot = TTICK(), w_full = 0, w_op = 0, n_st = 0, n_hit = 0;
         for (;;) {
-            mbar_wait(&ring.full[s], parity);
+            TWAIT(w_full, &ring.full[s], parity);
             Stage<0>& st = ring.stage[s];
             const uint32_t n = st.n, last = st.last, first = st.first;
             const int work = st.work;
@@ -195,11 +246,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             }
             const int nh = n > (uint32_t)kKS ? 2 : 1;
             for (int h = 0; h < nh; h++) {
-                mbar_wait(&sm.op_empty[os], (op_round & 1u) ^ 1u);
+                TWAIT(w_op, &sm.op_empty[os], (op_round & 1u) ^ 1u);
+                n_st++;
                 OpStage& op = sm.op[os];
                 float* whi = &op.Whi[b][0][0];
                 float* wlo = &op.Wlo[b][0][0];
-                {   // the block's 16 rows of both parts start as zeros (instances that miss the block stay zero)
+                if (!(F3DGS_TC_DIAG & 4)) {   // the block's 16 rows of both parts start as zeros (instances that miss the block stay zero)
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
@@ -208,12 +260,20 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
                     }
                 }
                 __syncwarp();
-                if (!blk_done && n > 0) {
+                if (!blk_done && n > 0 && !(F3DGS_TC_DIAG & 2)) {
                     const int e0 = h * kKS;
                     bool hit = false;
-                    if (lane < kKS && e0 + lane < (int)n)
+                    if (lane < kKS && e0 + lane < (int)n) {
+#if F3DGS_TC_BLOCK_EXACT
                         hit = footprint_hits_rect(st.rec0[e0 + lane], st.rec1[e0 + lane], fbx0, fbx0 + 7.f, fby0, fby0 + 3.f);
+#else
+                        const float4 r0 = st.rec0[e0 + lane];
+                        hit = (r0.x + r0.z >= fbx0) && (r0.x - r0.z <= fbx0 + 7.f) && (r0.y + r0.w >= fby0) &&
+                              (r0.y - r0.w <= fby0 + 3.f);
+#endif
+                    }
                     uint32_t am = __ballot_sync(0xffffffffu, hit);
+                    if (kTimingTc) n_hit += __popc(am);
                     while (am) {
                         // up to 4 instances per trip, branch-free alpha evaluation (see composite_fwd.cu)
                         int kk[4];
@@ -235,18 +295,30 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
                             const float av = fminf(0.99f, r1.w * expf(power));
                             al[u] = (vk[u] && !(power > 0.0f) && !(av < 1.0f / 255.0f)) ? av : 0.f;
                         }
+                        // The T recurrence of the (up to) four instances, written WITHOUT control flow: an empty slot has
+                        // alpha = 0 and changes nothing.  The only true dependency between consecutive instances is
+                        // T -> test_T -> T (and `done`); everything else (colour / depth accumulation, the hi / lo split,
+                        // the stores) then overlaps across the four.  With the `break` / `if (any blend)` branches of
+                        // the first version the warp ran one dependent chain per instance: 408 cycles per hit, 21% of the
+                        // cycles issuing (ncu source counters), and bounded the whole kernel.
+                        float4 r2v[4];
+                        uint32_t lpv[4];
+                        float wg[4];
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            if (!vk[u]) break;  // warp-uniform, only in the last trip
-                            const float4 r2 = st.rec2[e0 + kk[u]];
-                            const uint32_t lp = st.listpos[e0 + kk[u]];
+                            r2v[u] = st.rec2[e0 + kk[u]];
+                            lpv[u] = st.listpos[e0 + kk[u]];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float4 r2 = r2v[u];
                             const float alpha = al[u];
                             const float test_T = T * (1 - alpha);
                             const bool act = !done && alpha > 0.f;
                             const bool stop = act && (test_T < 0.0001f);  // reference: done = true, not blended
                             const bool blend = act && !stop;
                             done = done || stop;
-                            const float wgt = blend ? alpha * T : 0.f;
+                            wg[u] = blend ? alpha * T : 0.f;
                             const float nCr = Cr + r2.x * alpha * T;  // reference forward.cu:362-368
                             const float nCg = Cg + r2.y * alpha * T;
                             const float nCb = Cb + r2.z * alpha * T;
@@ -256,12 +328,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
                             Cb = blend ? nCb : Cb;
                             Dp = blend ? nDp : Dp;
                             T = blend ? test_T : T;
-                            last_contrib = blend ? lp : last_contrib;
-                            if (__any_sync(0xffffffffu, blend)) {
-                                const float hi = tf32_hi(wgt);
+                            last_contrib = blend ? lpv[u] : last_contrib;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (vk[u]) {  // warp-uniform
+                                const float hi = tf32_hi(wg[u]);
                                 const int o = sw32b_idx(kk[u], lane);
                                 whi[o] = hi;
-                                wlo[o] = wgt - hi;
+                                wlo[o] = wg[u] - hi;
                             }
                         }
                     }
@@ -288,13 +363,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             }
             if (++s == kStages) { s = 0; parity ^= 1; }
         }
+        TDUMP(TTICK() - t_tot, w_full, w_op, n_st, n_hit, 0);
     } else if (warp >= kConv0 && warp < kConv0 + kConvN) {
         // ==================================================================== convert warps
         const int cw = warp - kConv0;
         int s = 0;
         uint32_t parity = 0, seq = 0;  // seq: operand stages since the start (this warp serves seq % kConvN == cw)
+        long long t_tot = TTICK(), w_full = 0, w_op = 0, n_st = 0;
         for (;;) {
-            mbar_wait(&ring.full[s], parity);
+            TWAITS(w_full, &ring.full[s], parity, 64);
             const Stage<0>& st = ring.stage[s];
             const uint32_t n = st.n;
             const int work = st.work;
@@ -305,27 +382,37 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             for (int h = 0; h < nh; h++, seq++) {
                 if ((int)(seq % kConvN) != cw) continue;
                 const int cnt = max(0, min(kKS, (int)n - h * kKS));
-                float4 v[kKS];
-#pragma unroll
-                for (int r = 0; r < kKS; r++) {
-                    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < cnt && 4 * lane < row_floats)
-                        v[r] = ld_nc_f4(args.features + (size_t)st.gid[h * kKS + r] * C + chunk_off + 4 * lane);
-                }
                 const int os = (int)(seq % kOpStages);
-                mbar_wait(&sm.op_empty[os], ((seq / kOpStages) & 1u) ^ 1u);
                 OpStage& op = sm.op[os];
                 float* fhi = &op.Fhi[lane >> 3][0][0];
                 float* flo = &op.Flo[lane >> 3][0][0];
+                bool waited = false;
 #pragma unroll
-                for (int r = 0; r < kKS; r++) {
-                    if (r < cnt) {
-                        const float4 hi = make_float4(tf32_hi(v[r].x), tf32_hi(v[r].y), tf32_hi(v[r].z), tf32_hi(v[r].w));
-                        const float4 lo = make_float4(v[r].x - hi.x, v[r].y - hi.y, v[r].z - hi.z, v[r].w - hi.w);
-                        // 16-byte piece (lane & 7) of the row: 32-byte chunk ((lane & 7) >> 1) ^ (r & 3), half (lane & 1)
-                        const int o = r * 32 + (((((lane & 7) >> 1) ^ (r & 3)) << 1) | (lane & 1)) * 4;
-                        *reinterpret_cast<float4*>(fhi + o) = hi;
-                        *reinterpret_cast<float4*>(flo + o) = lo;
+                for (int r0 = 0; r0 < kKS; r0 += kConvBatch) {
+                    float4 v[kConvBatch];
+#pragma unroll
+                    for (int i = 0; i < kConvBatch; i++) {
+                        const int r = r0 + i;
+                        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < cnt && 4 * lane < row_floats && !(F3DGS_TC_DIAG & 8))
+                            v[i] = ld_nc_f4(args.features + (size_t)st.gid[h * kKS + r] * C + chunk_off + 4 * lane);
+                    }
+                    if (!waited) {  // the loads are in flight while the stage's previous MMAs drain
+                        TWAITS(w_op, &sm.op_empty[os], ((seq / kOpStages) & 1u) ^ 1u, 128);
+                        n_st++;
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kConvBatch; i++) {
+                        const int r = r0 + i;
+                        if (r < cnt) {
+                            const float4 hi = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                            const float4 lo = make_float4(v[i].x - hi.x, v[i].y - hi.y, v[i].z - hi.z, v[i].w - hi.w);
+                            // 16-byte piece (lane & 7) of the row: 32-byte chunk ((lane & 7) >> 1) ^ (r & 3), half (lane & 1)
+                            const int o = r * 32 + (((((lane & 7) >> 1) ^ (r & 3)) << 1) | (lane & 1)) * 4;
+                            *reinterpret_cast<float4*>(fhi + o) = hi;
+                            *reinterpret_cast<float4*>(flo + o) = lo;
+                        }
                     }
                 }
                 fence_async_smem();
@@ -336,12 +423,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             if (lane == 0) mbar_arrive(&ring.empty[s]);
             if (++s == kStages) { s = 0; parity ^= 1; }
         }
+        TDUMP(TTICK() - t_tot, w_full, w_op, n_st, 0, 0);
     } else if (warp >= kEpi0) {
         // ==================================================================== epilogue warps
         const int ew = warp - kEpi0;
+        long long t_tot = TTICK(), w_full = 0, n_tiles = 0;
         for (uint32_t seq = 0;; seq++) {
-            const int buf = (int)(seq & 1u);
-            mbar_wait(&sm.tmem_full[buf], (seq >> 1) & 1u);
+            const int buf = (int)(seq % kAccBufs);
+            TWAITS(w_full, &sm.tmem_full[buf], (seq / kAccBufs) & 1u, 512);
+            n_tiles++;
             tc_fence_after();
             const int work = *reinterpret_cast<volatile int32_t*>(&sm.tile_work[buf]);
             if (work < 0) break;
@@ -379,6 +469,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);
         }
+        TDUMP(TTICK() - t_tot, w_full, n_tiles, 0, 0, 0);
     }
 
     // ======================================================================== teardown
@@ -386,7 +477,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) composite_fwd_tc_kernel(const F
     __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc_512(tmem);
+        tmem_dealloc<kTmemCols>(tmem);
     }
 }
 
@@ -426,9 +517,31 @@ cudaError_t launch_composite_fwd_tc(const ViewParams& vp, const uint2* ranges, c
     a.vec_store = (vp.W % 8 == 0 && (reinterpret_cast<uintptr_t>(out_feature) & 31) == 0) ? 2 : 0;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles * a.pa.chunks, sms_of_device[dev].load());
+    const int grid = min(a.pa.num_tiles * a.pa.chunks, kNCta * sms_of_device[dev].load());
+    static long long* dbg = nullptr;
+    const bool timing = kTimingTc && getenv("F3DGS_TIMING") != nullptr;
+    if (timing && !dbg) cudaMalloc(&dbg, 512 * 32 * 8 * sizeof(long long));
+    a.dbg = timing ? dbg : nullptr;
+    if (timing) cudaMemsetAsync(dbg, 0, 512 * 32 * 8 * sizeof(long long), s);
     composite_fwd_tc_kernel<<<grid, kThreadsTc, smem, s>>>(a);
     g_launches++;
+    if (timing) {
+        static long long host[512 * 32 * 8];
+        cudaMemcpyAsync(host, dbg, sizeof(host), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        auto avg = [&](int w0, int nw, int i) {
+            double t = 0;
+            for (int c = 0; c < grid; c++) for (int w = w0; w < w0 + nw; w++) t += host[((size_t)c * 32 + w) * 8 + i];
+            return t / ((double)grid * nw);
+        };
+        fprintf(stderr, "[f3dgs timing fwd_tc] per-warp mean cycles: producer %.0f | mma total %.0f wait_rec %.0f wait_tmem %.0f wait_opfull %.0f stages %.0f | "
+                        "alpha total %.0f wait_rec %.0f wait_opempty %.0f stages %.0f hits %.0f | convert total %.0f wait_rec %.0f wait_opempty %.0f stages %.0f | "
+                        "epilogue total %.0f wait_tmemfull %.0f tiles %.0f\n",
+                avg(0, 1, 0), avg(kMmaWarp, 1, 0), avg(kMmaWarp, 1, 1), avg(kMmaWarp, 1, 2), avg(kMmaWarp, 1, 3), avg(kMmaWarp, 1, 4),
+                avg(kAlpha0, kAlphaN, 0), avg(kAlpha0, kAlphaN, 1), avg(kAlpha0, kAlphaN, 2), avg(kAlpha0, kAlphaN, 3), avg(kAlpha0, kAlphaN, 4),
+                avg(kConv0, kConvN, 0), avg(kConv0, kConvN, 1), avg(kConv0, kConvN, 2), avg(kConv0, kConvN, 3),
+                avg(kEpi0, kEpiN, 0), avg(kEpi0, kEpiN, 1), avg(kEpi0, kEpiN, 2));
+    }
     return cudaGetLastError();
 }
 
