@@ -175,6 +175,10 @@ __device__ __forceinline__ void alpha_extent(float A, float B, float C, float op
     ey = sqrtf(tau * A / det) + 0.01f;
 }
 
+// shared-memory staging of SH rows (both preprocess kernels)
+constexpr int kBwdBlock = 128;
+__host__ __device__ constexpr int bwd_row_stride(int row_floats) { return row_floats | 1; }  // odd stride: no bank conflicts
+
 __global__ void __launch_bounds__(256)
 preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const float* __restrict__ scales,
                       const float* __restrict__ rotations, const float* __restrict__ opacities,
@@ -182,7 +186,28 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
                       const float* __restrict__ colors_precomp, bool prefiltered, int* __restrict__ radii,
                       SplatRec* __restrict__ rec, float* __restrict__ cov3D, uint8_t* __restrict__ clamped,
                       uint32_t* __restrict__ tiles_touched) {
+    // SH rows (12 M bytes per Gaussian) come in through shared memory with coalesced 128-bit loads; each thread then reads
+    // its own padded row (see preprocess_bwd_kernel).  The arithmetic on the values is unchanged.
+    extern __shared__ float fwd_sh_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row_floats = vp.M * 3, stride = bwd_row_stride(row_floats);
+    if (shs != nullptr) {
+        const int block_base = blockIdx.x * blockDim.x;
+        const int rows_here = min((int)blockDim.x, vp.P - block_base);
+        const float* src = shs + (size_t)block_base * row_floats;
+        if ((row_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
+            const int q_per_row = row_floats >> 2;
+            for (int i = threadIdx.x; i < rows_here * q_per_row; i += blockDim.x) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+                float* d = fwd_sh_rows + (i / q_per_row) * stride + (i % q_per_row) * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < rows_here * row_floats; i += blockDim.x)
+                fwd_sh_rows[(i / row_floats) * stride + (i % row_floats)] = __ldg(src + i);
+        }
+        __syncthreads();
+    }
     if (idx >= vp.P) return;
     int my_radii = 0;
     uint32_t my_tiles = 0;
@@ -230,7 +255,7 @@ preprocess_fwd_kernel(ViewParams vp, const float* __restrict__ means3D, const fl
         SplatRec r;
         uint8_t cb = 0;
         if (colors_precomp == nullptr) {
-            F3 col = sh_to_rgb(vp.D, shs + (size_t)idx * vp.M * 3, p_orig, vp.cam_pos, cb);
+            F3 col = sh_to_rgb(vp.D, fwd_sh_rows + threadIdx.x * stride, p_orig, vp.cam_pos, cb);
             r.r = col.x; r.g = col.y; r.b = col.z;
         } else {
             r.r = colors_precomp[3 * idx]; r.g = colors_precomp[3 * idx + 1]; r.b = colors_precomp[3 * idx + 2];
@@ -286,8 +311,14 @@ __device__ __forceinline__ void put(float* __restrict__ dst, float v) {
     else *dst = v;
 }
 
+// The 12 M bytes of SH coefficients per Gaussian (192 B at M = 16) are the widest operand of this kernel, read once and --
+// as gradients -- written once (read-modify-written in ACCUM mode).  One thread per Gaussian touching its own row gives 32
+// rows x 4 bytes per warp instruction, i.e. one useful word per 32-byte sector.  So the block stages both directions in
+// shared memory: rows come in and go out with coalesced 128-bit accesses, each thread works on its own (padded,
+// conflict-free) row in between.
+
 template <bool ACCUM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBwdBlock)
 preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const int* __restrict__ radii,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -296,8 +327,34 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
                       const float* __restrict__ dL_dcolor, float* __restrict__ dL_dcov3D,
                       float* __restrict__ dL_dsh, float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
                       const float* __restrict__ dL_dz, float* __restrict__ grad_accum, float* __restrict__ vis_count) {
+    extern __shared__ float bwd_smem[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= vp.P || !(radii[idx] > 0)) return;
+    const int row_floats = vp.M * 3, stride = bwd_row_stride(row_floats);
+    float* sh_rows = bwd_smem;                              // [kBwdBlock][stride] coefficients in
+    float* dsh_rows = bwd_smem + kBwdBlock * stride;        // [kBwdBlock][stride] gradients out
+    uint8_t* vis = reinterpret_cast<uint8_t*>(bwd_smem + 2 * kBwdBlock * stride);
+    const int block_base = blockIdx.x * kBwdBlock;
+    const int rows_here = min(kBwdBlock, vp.P - block_base);
+    const bool visible = idx < vp.P && radii[idx] > 0;
+    if (shs != nullptr) {
+        vis[threadIdx.x] = visible ? 1 : 0;
+        const float* src = shs + (size_t)block_base * row_floats;
+        if ((row_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
+            const int q_per_row = row_floats >> 2;
+            for (int i = threadIdx.x; i < rows_here * q_per_row; i += kBwdBlock) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+                float* d = sh_rows + (i / q_per_row) * stride + (i % q_per_row) * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < rows_here * row_floats; i += kBwdBlock)
+                sh_rows[(i / row_floats) * stride + (i % row_floats)] = __ldg(src + i);
+        }
+        // gradient rows start as zeros: degrees above the active one are not written by the owner thread
+        for (int i = threadIdx.x; i < kBwdBlock * stride; i += kBwdBlock) dsh_rows[i] = 0.f;
+        __syncthreads();
+    }
+    if (visible) {
     if (ACCUM && grad_accum != nullptr) {
         const float ux = dL_dmean2D[3 * idx], uy = dL_dmean2D[3 * idx + 1];
         grad_accum[idx] += sqrtf(ux * ux + uy * uy);
@@ -389,8 +446,8 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
 
     // ---- SH backward (reference backward.cu:20-139)
     if (shs != nullptr) {
-        const float* sh = shs + (size_t)idx * vp.M * 3;
-        float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
+        const float* sh = sh_rows + threadIdx.x * stride;
+        float* dsh = dsh_rows + threadIdx.x * stride;
         const float* cam = vp.cam_pos;
         F3 dir_orig = {mx - cam[0], my - cam[1], mz - cam[2]};
         const float inv_len = 1.0f / sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -406,9 +463,9 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
 #define WR(k, coef)                                                  \
     do {                                                             \
         const float cf_ = (coef);                                    \
-        put<ACCUM>(dsh + 3 * (k), cf_ * dRGB[0]);                    \
-        put<ACCUM>(dsh + 3 * (k) + 1, cf_ * dRGB[1]);                \
-        put<ACCUM>(dsh + 3 * (k) + 2, cf_ * dRGB[2]);                \
+        dsh[3 * (k)] = cf_ * dRGB[0];                                \
+        dsh[3 * (k) + 1] = cf_ * dRGB[1];                            \
+        dsh[3 * (k) + 2] = cf_ * dRGB[2];                            \
     } while (0)
         WR(0, kSH_C0);
         if (deg > 0) {
@@ -530,6 +587,34 @@ preprocess_bwd_kernel(ViewParams vp, const float* __restrict__ means3D, const in
         }
         reinterpret_cast<float4*>(dL_drot)[idx] = dq;
     }
+    }  // visible
+    if (shs != nullptr) {
+        // coalesced write-out of the block's gradient rows (rows of culled Gaussians stay untouched: zero / unchanged)
+        __syncthreads();
+        float* dst = dL_dsh + (size_t)block_base * row_floats;
+        if ((row_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0) {
+            const int q_per_row = row_floats >> 2;
+            for (int i = threadIdx.x; i < rows_here * q_per_row; i += kBwdBlock) {
+                const int row = i / q_per_row;
+                if (!vis[row]) continue;
+                const float* g = dsh_rows + row * stride + (i % q_per_row) * 4;
+                float4 v = make_float4(g[0], g[1], g[2], g[3]);
+                float4* o = reinterpret_cast<float4*>(dst) + i;
+                if (ACCUM) {
+                    const float4 old = *o;
+                    v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                }
+                *o = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < rows_here * row_floats; i += kBwdBlock) {
+                const int row = i / row_floats;
+                if (!vis[row]) continue;
+                const float g = dsh_rows[row * stride + (i % row_floats)];
+                dst[i] = ACCUM ? dst[i] + g : g;
+            }
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------- launchers
@@ -539,7 +624,9 @@ void launch_preprocess_fwd(const ViewParams& vp, const float* means3D, const flo
                            int* radii, SplatRec* rec, float* cov3D, uint8_t* clamped,
                            uint32_t* tiles_touched, cudaStream_t s) {
     if (vp.P <= 0) return;
-    preprocess_fwd_kernel<<<(vp.P + 255) / 256, 256, 0, s>>>(vp, means3D, scales, rotations, opacities, shs,
+    constexpr int kFwdBlock = 128;
+    const size_t smem = shs ? (size_t)kFwdBlock * bwd_row_stride(vp.M * 3) * sizeof(float) : 0;
+    preprocess_fwd_kernel<<<(vp.P + kFwdBlock - 1) / kFwdBlock, kFwdBlock, smem, s>>>(vp, means3D, scales, rotations, opacities, shs,
                                                            cov3D_precomp, colors_precomp, prefiltered, radii,
                                                            rec, cov3D, clamped, tiles_touched);
     g_launches++;
@@ -552,12 +639,22 @@ void launch_preprocess_bwd(const ViewParams& vp, const float* means3D, const int
                            float* dL_dscale, float* dL_drot, const float* dL_dz, cudaStream_t s, bool accumulate,
                            float* grad_accum, float* denom) {
     if (vp.P <= 0) return;
+    const size_t smem = shs ? (size_t)2 * kBwdBlock * bwd_row_stride(vp.M * 3) * sizeof(float) + kBwdBlock : 0;
+    static std::atomic<int> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && !((attr_set.load() >> (dev & 31)) & 1)) {  // once per device; harmless if repeated
+        cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(preprocess_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set.fetch_or(1 << (dev & 31));
+    }
+    const int grid = (vp.P + kBwdBlock - 1) / kBwdBlock;
     if (accumulate)
-        preprocess_bwd_kernel<true><<<(vp.P + 255) / 256, 256, 0, s>>>(
+        preprocess_bwd_kernel<true><<<grid, kBwdBlock, smem, s>>>(
             vp, means3D, radii, shs, clamped, scales, rotations, cov3D, dL_dmean2D, dL_dconic, dL_dmean3D, dL_dcolor,
             dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, grad_accum, denom);
     else
-        preprocess_bwd_kernel<false><<<(vp.P + 255) / 256, 256, 0, s>>>(
+        preprocess_bwd_kernel<false><<<grid, kBwdBlock, smem, s>>>(
             vp, means3D, radii, shs, clamped, scales, rotations, cov3D, dL_dmean2D, dL_dconic, dL_dmean3D, dL_dcolor,
             dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dz, nullptr, nullptr);
     g_launches++;
