@@ -543,6 +543,31 @@ int f3dgs_backward_accum(int P, int D, int M, int R, int C, const float* backgro
     return 0;
 }
 
+int f3dgs_feature_resize_fwd(int C, int H, int W, int Hg, int Wg, const float* feature_map, const float* gt,
+                             float grad_scale, float* out, float* loss_sum, void* cuda_stream) {
+    t_error.clear();
+    if (C < 0 || H <= 0 || W <= 0 || Hg <= 0 || Wg <= 0)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_feature_resize_fwd: bad sizes");
+    if (C == 0) return 0;
+    if (!feature_map || !out) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_feature_resize_fwd: NULL pointer");
+    cudaError_t e = launch_feature_resize_fwd(C, H, W, Hg, Wg, feature_map, gt, grad_scale, out, loss_sum,
+                                              (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("feature_resize_fwd: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int f3dgs_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const float* dout, float* dL_dfeature_map,
+                             void* cuda_stream) {
+    t_error.clear();
+    if (C < 0 || H <= 0 || W <= 0 || Hg <= 0 || Wg <= 0)
+        return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_feature_resize_bwd: bad sizes");
+    if (C == 0) return 0;
+    if (!dout || !dL_dfeature_map) return fail(F3DGS_ERR_INVALID_ARGUMENT, "f3dgs_feature_resize_bwd: NULL pointer");
+    cudaError_t e = launch_feature_resize_bwd(C, H, W, Hg, Wg, dout, dL_dfeature_map, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return fail(F3DGS_ERR_CUDA, std::string("feature_resize_bwd: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 int f3dgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                        uint8_t* present, void* cuda_stream) {
     (void)projmatrix;  // the reference's frustum side test is commented out (auxiliary.h:160)

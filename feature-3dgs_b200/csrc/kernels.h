@@ -81,4 +81,9 @@ cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, cons
                                  float* dL_dopacity, float* dL_dcolor, float* dL_dfeature, float* dL_dz,
                                  int* work_counter, cudaStream_t s);
 
+// ---- feature_head.cu
+cudaError_t launch_feature_resize_fwd(int C, int H, int W, int Hg, int Wg, const float* fm, const float* gt,
+                                      float grad_scale, float* out, float* loss_sum, cudaStream_t s);
+cudaError_t launch_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const float* dout, float* dfm, cudaStream_t s);
+
 }  // namespace f3dgs

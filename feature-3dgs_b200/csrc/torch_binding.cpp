@@ -248,6 +248,77 @@ torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, tor
     return present;
 }
 
+// ---- post-raster feature head (include/f3dgs_b200.h: f3dgs_feature_resize_fwd / _bwd) ----------------------------
+// -> (out [C,Hg,Wg], loss_sum [1]); with gt: out = sign(resized - gt) * grad_scale and loss_sum = sum |resized - gt|
+std::tuple<torch::Tensor, torch::Tensor> featureResizeFwd(const torch::Tensor& feature_map, const torch::Tensor& gt,
+                                                          int64_t Hg, int64_t Wg, double grad_scale) {
+    TORCH_CHECK(feature_map.is_cuda() && feature_map.dim() == 3 && feature_map.scalar_type() == torch::kFloat32,
+                "feature_map must be a float32 CUDA tensor [C,H,W]");
+    const c10::cuda::CUDAGuard guard(feature_map.device());
+    auto fm = feature_map.contiguous();
+    const int C = fm.size(0), H = fm.size(1), W = fm.size(2);
+    const bool has_gt = gt.defined() && gt.numel() > 0;
+    torch::Tensor g;
+    if (has_gt) {
+        TORCH_CHECK(gt.is_cuda() && gt.scalar_type() == torch::kFloat32 && gt.dim() == 3 && gt.size(0) == C &&
+                        gt.size(1) == Hg && gt.size(2) == Wg, "gt must be a float32 CUDA tensor [C,Hg,Wg]");
+        g = gt.contiguous();
+    }
+    torch::Tensor out = torch::empty({C, Hg, Wg}, fm.options());
+    torch::Tensor loss = torch::zeros({1}, fm.options());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check_rc(f3dgs_feature_resize_fwd(C, H, W, (int)Hg, (int)Wg, fptr(fm), has_gt ? fptr(g) : nullptr, (float)grad_scale,
+                                      out.data_ptr<float>(), loss.data_ptr<float>(), (void*)stream),
+             "f3dgs_feature_resize_fwd");
+    return std::make_tuple(out, loss);
+}
+
+torch::Tensor featureResizeBwd(const torch::Tensor& dout, int64_t H, int64_t W) {
+    TORCH_CHECK(dout.is_cuda() && dout.dim() == 3 && dout.scalar_type() == torch::kFloat32,
+                "dout must be a float32 CUDA tensor [C,Hg,Wg]");
+    const c10::cuda::CUDAGuard guard(dout.device());
+    auto d = dout.contiguous();
+    const int C = d.size(0), Hg = d.size(1), Wg = d.size(2);
+    torch::Tensor dfm = torch::empty({C, H, W}, d.options());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check_rc(f3dgs_feature_resize_bwd(C, (int)H, (int)W, Hg, Wg, fptr(d), dfm.data_ptr<float>(), (void*)stream),
+             "f3dgs_feature_resize_bwd");
+    return dfm;
+}
+
+// ---- activation prologue + fused optimizer step (f3dgs_activate / f3dgs_adam_step): in-place on the caller's tensors
+void activateParams(const torch::Tensor& raw_opacity, const torch::Tensor& raw_scaling, const torch::Tensor& raw_rotation,
+                    const torch::Tensor& f_dc, const torch::Tensor& f_rest, torch::Tensor opacity, torch::Tensor scales,
+                    torch::Tensor rotations, torch::Tensor shs) {
+    TORCH_CHECK(raw_opacity.is_cuda(), "parameters must be CUDA tensors (this build has no CPU path)");
+    const c10::cuda::CUDAGuard guard(raw_opacity.device());
+    const int P = raw_opacity.size(0);
+    const int M = shs.defined() && shs.numel() ? (int)shs.size(1) : 0;
+    for (const torch::Tensor* t : std::initializer_list<const torch::Tensor*>{&raw_opacity, &raw_scaling, &raw_rotation, &f_dc, &f_rest, &opacity, &scales, &rotations, &shs})
+        TORCH_CHECK(!t->defined() || t->numel() == 0 || (t->is_cuda() && t->is_contiguous() && t->scalar_type() == torch::kFloat32),
+                    "activate: tensors must be contiguous float32 CUDA tensors");
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check_rc(f3dgs_activate(P, M, fptr(raw_opacity), fptr(raw_scaling), fptr(raw_rotation), fptr(f_dc), fptr(f_rest),
+                            const_cast<float*>(fptr(opacity)), const_cast<float*>(fptr(scales)),
+                            const_cast<float*>(fptr(rotations)), const_cast<float*>(fptr(shs)), (void*)stream),
+             "f3dgs_activate");
+}
+
+void adamStep(int64_t kind, torch::Tensor param, const torch::Tensor& grad_activated, torch::Tensor exp_avg,
+              torch::Tensor exp_avg_sq, int64_t M, double lr, double beta1, double beta2, double eps, int64_t step) {
+    TORCH_CHECK(param.is_cuda(), "parameters must be CUDA tensors (this build has no CPU path)");
+    const c10::cuda::CUDAGuard guard(param.device());
+    for (const torch::Tensor* t : std::initializer_list<const torch::Tensor*>{&param, &grad_activated, &exp_avg, &exp_avg_sq})
+        TORCH_CHECK(t->is_cuda() && t->is_contiguous() && t->scalar_type() == torch::kFloat32,
+                    "adam_step: tensors must be contiguous float32 CUDA tensors");
+    TORCH_CHECK(exp_avg.numel() == param.numel() && exp_avg_sq.numel() == param.numel(), "adam_step: state shape mismatch");
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check_rc(f3dgs_adam_step((int)kind, (size_t)param.numel(), (int)M, param.data_ptr<float>(), fptr(grad_activated),
+                             exp_avg.data_ptr<float>(), exp_avg_sq.data_ptr<float>(), (float)lr, (float)beta1, (float)beta2,
+                             (float)eps, (int)step, (void*)stream),
+             "f3dgs_adam_step");
+}
+
 // Read-only views into the opaque buffers for the parity harness (not part of the reference API).
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> debugViews(
     const torch::Tensor& geomBuffer, const torch::Tensor& binningBuffer, const torch::Tensor& imgBuffer, int P,
@@ -274,6 +345,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("mark_visible", &markVisible);
     m.def("rasterize_gaussians_backward_accum", &RasterizeGaussiansBackwardAccumCUDA);
+    m.def("feature_resize_fwd", &featureResizeFwd);
+    m.def("feature_resize_bwd", &featureResizeBwd);
+    m.def("activate", &activateParams);
+    m.def("adam_step", &adamStep);
     m.def("backward_scratch_bytes", [](int P) { return (unsigned long long)f3dgs_backward_scratch_bytes(P); });
     m.def("debug_views", &debugViews);
     m.def("launch_count", []() { return (unsigned long long)f3dgs_launch_count(); });

@@ -133,6 +133,46 @@ int f3dgs_backward_accum(int P, int D, int M, int R, int C,
                          float* dL_drot, float* dL_dmean2D_out, float* grad_accum, float* denom,
                          void* composite_done_event, int debug, void* cuda_stream);
 
+/* ==== callers either side of the rasterizer (SURVEY.md section 8 f): additive entry points ======================= */
+
+/* ---- post-raster feature head: reference train.py:98-104 ---------------------------------------------------------
+ * F.interpolate(feature_map[C,H,W] -> [C,Hg,Wg], mode='bilinear', align_corners=True) fused with l1_loss against the
+ * teacher map and its gradient.
+ *   f3dgs_feature_resize_fwd  gt != NULL: out[C,Hg,Wg] = sign(resized - gt) * grad_scale  (dL/d resized for
+ *                             L = grad_scale * sum |resized - gt|; pass weight / (C*Hg*Wg) for the weighted mean) and
+ *                             *loss_sum += sum |resized - gt|  (device float, caller-zeroed, may be NULL);
+ *                             gt == NULL: out = resized map (decoder path: the 1x1 convolution of
+ *                             models/networks.py:107-119 runs between the two calls as a library GEMM).
+ *   f3dgs_feature_resize_bwd  dL_dfeature_map[C,H,W] = resize^T(dout[C,Hg,Wg]); every element is written (gather, no
+ *                             atomics, no zero fill needed).
+ */
+int f3dgs_feature_resize_fwd(int C, int H, int W, int Hg, int Wg, const float* feature_map, const float* gt,
+                             float grad_scale, float* out, float* loss_sum, void* cuda_stream);
+int f3dgs_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const float* dout, float* dL_dfeature_map,
+                             void* cuda_stream);
+
+/* ---- activation prologue: reference scene/gaussian_model.py:98-121 ------------------------------------------------
+ * opacity = sigmoid(raw_opacity[P]); scales = exp(raw_scaling[P,3]); rotations = normalize(raw_rotation[P,4]);
+ * shs[P,M,3] = cat(features_dc[P,1,3], features_rest[P,M-1,3]).  Any raw pointer may be NULL (group skipped). */
+int f3dgs_activate(int P, int M, const float* raw_opacity, const float* raw_scaling, const float* raw_rotation,
+                   const float* features_dc, const float* features_rest, float* opacity, float* scales,
+                   float* rotations, float* shs, void* cuda_stream);
+
+/* ---- fused optimizer step: reference scene/gaussian_model.py:163-190 (torch.optim.Adam, one call per group) --------
+ * `grad_activated` is the gradient w.r.t. the ACTIVATED tensor as the rasterizer's backward produces it; `kind` names
+ * the activation whose Jacobian is applied before the Adam update of the raw parameter (n elements, in place):
+ *   IDENTITY (xyz, semantic features)   SIGMOID (opacity)   EXP (scaling)   NORMALIZE4 (rotation, n % 4 == 0)
+ *   SH_DC / SH_REST: the raw parameter is features_dc [P,1,3] / features_rest [P,M-1,3], the gradient the [P,M,3] SH tensor.
+ * step >= 1 is the 1-based Adam step count of the group (bias correction). */
+#define F3DGS_PARAM_IDENTITY 0
+#define F3DGS_PARAM_SIGMOID 1
+#define F3DGS_PARAM_EXP 2
+#define F3DGS_PARAM_NORMALIZE4 3
+#define F3DGS_PARAM_SH_DC 4
+#define F3DGS_PARAM_SH_REST 5
+int f3dgs_adam_step(int kind, size_t n, int M, float* param, const float* grad_activated, float* exp_avg,
+                    float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step, void* cuda_stream);
+
 /* ---- markVisible: reference rasterizer_impl.cu:141-153 (checkFrustum :54-66) --------------
  * present[i] = (view-space z of means3D[i] > 0.2).  `present` is P bytes (0/1). */
 int f3dgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
