@@ -254,6 +254,10 @@ def main():
             means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], shs=t["shs"],
             semantic_feature=t["semantic_feature"] if C else None, scales=t["scales"], rotations=t["rotations"])
 
+    # teacher feature map at the teacher's resolution (reference train.py:99: viewpoint_cam.semantic_feature), resident
+    Hg, Wg = max(int(round(H / 2.25)), 1), max(int(round(W / 2.25)), 1)
+    gt_feat = torch.rand(C, Hg, Wg, device=dev) if C else None
+
     stats = {}
     use_batch = args.impl == "ours" and args.api == "batch" and not fwd_only
     if args.impl == "ours" and not fwd_only:
@@ -273,18 +277,25 @@ def main():
                 stats["radii"] = radii
             vb.all_reduce()
 
+        from diff_gaussian_rasterization import feature_head as fh
+
         def step_e2e_batch():
+            # the reference's loss structure (train.py:96-104): a colour term on the rendered image through autograd
+            # (small tensors) + the L1 feature loss against the teacher map after the bilinear resize -- the latter through
+            # the fused feature head (csrc/feature_head.cu), which also returns dL/dfeature_map
             vb.zero_()
             total = torch.zeros((), device=dev)
             for i, cam in enumerate(cams):
                 cam_stage[i].copy_(cam_host[i], non_blocking=True)  # H2D of this view's camera
                 color, feat, radii, depth, ctx = vb.forward(settings_of(cam, cam_stage[i]))
-                outs = [color.requires_grad_(), depth.requires_grad_()] + ([feat.requires_grad_()] if C else [])
+                outs = [color.requires_grad_(), depth.requires_grad_()]
                 loss = (outs[0] * gc).sum() + (outs[1] * gd).sum()
+                loss.backward()  # the user's colour / depth loss: autograd only over two small maps
+                gfeat = None
                 if C:
-                    loss = loss + (outs[2] * gf).sum()
-                loss.backward()  # the user's loss: autograd only over the three rendered maps
-                vb.backward(ctx, color.grad, feat.grad if C else None, depth.grad, last=(i == len(cams) - 1))
+                    lf, gfeat = fh.feature_l1_loss_and_grad(feat, gt_feat, 1.0)
+                    loss = loss.detach() + lf
+                vb.backward(ctx, color.grad, gfeat, depth.grad, last=(i == len(cams) - 1))
                 total = total + loss.detach()
             vb.all_reduce()
             return float(total.item())  # D2H read of the step's result
@@ -325,8 +336,10 @@ def main():
             cam_stage[i].copy_(cam_host[i], non_blocking=True)  # H2D of this view's camera
             color, feat, radii, depth = render(cam, cam_stage[i])
             loss = (color * gc).sum() + (depth * gd).sum()
-            if C:
-                loss = loss + (feat * gf).sum()
+            if C:  # the reference's feature loss, with the reference's own operators (train.py:100-104)
+                fm = torch.nn.functional.interpolate(feat.unsqueeze(0), size=(Hg, Wg), mode="bilinear",
+                                                     align_corners=True).squeeze(0)
+                loss = loss + torch.abs(fm - gt_feat).mean()
             loss.backward()
             total = total + loss.detach()
         flat.all_reduce()
@@ -424,8 +437,12 @@ def main():
                            "GaussianRasterizer autograd API (forward" + ("" if fwd_only else " + torch.autograd.backward") + ")"),
                    "other_api": other_api,
                    "e2e_moves": "per view: 35 floats of camera state from pinned host memory (H2D); per step: the scalar loss "
-                                "(D2H). Gaussian parameters, upstream-gradient weights and rendered maps stay in HBM (model "
-                                "state and loss inputs of a training loop, as in the reference train.py)"},
+                                "(D2H). Gaussian parameters, loss targets and rendered maps stay in HBM (model state and "
+                                "dataset cache of a training loop, as in the reference train.py)",
+                   "e2e_loss": ("colour/depth term sum(out * fixed weights) + the reference's feature loss (train.py:100-104): "
+                                "L1 against a resident teacher map at 1/2.25 resolution after a bilinear resize "
+                                "(align_corners=True). Autograd API / reference arm: PyTorch operators; batch API: the fused "
+                                "feature head (csrc/feature_head.cu)")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
