@@ -116,25 +116,25 @@ struct GatherTables {
     int Ky, Kx;
 };
 
-// one thread per element of the [C, H, W] gradient, x fastest
+// grid = (ceil(W / 256), C * H): one block per 256-pixel piece of one gradient row, so the row's y-table entries are
+// block-uniform and nothing is divided per element (a flat 64-bit index with % W, % H cost 2.0 ms at config 3 -- more than
+// the composite it follows; this form is bound by the 1 GB it writes)
 __global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, GatherTables t, const float* __restrict__ dout,
-                                                         float* __restrict__ dfm) {
-    const size_t n = (size_t)g.C * g.H * g.W;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = (int)(i % g.W);
-    const int y = (int)((i / g.W) % g.H);
-    const int c = (int)(i / ((size_t)g.W * g.H));
+                                                         float* __restrict__ dfm, int row0) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int row = row0 + blockIdx.y;   // c * H + y
+    const int c = row / g.H, y = row - c * g.H;
+    if (x >= g.W) return;
     const float* p = dout + (size_t)c * g.Hg * g.Wg;
     const int ny = t.cnt_y[y], nx = t.cnt_x[x];
     float acc = 0.f;
     for (int a = 0; a < ny; a++) {
-        const float* row = p + (size_t)t.idx_y[(size_t)y * t.Ky + a] * g.Wg;
+        const float* orow = p + (size_t)t.idx_y[(size_t)y * t.Ky + a] * g.Wg;
         float r = 0.f;
-        for (int b = 0; b < nx; b++) r += t.w_x[(size_t)x * t.Kx + b] * __ldg(row + t.idx_x[(size_t)x * t.Kx + b]);
+        for (int b = 0; b < nx; b++) r += t.w_x[(size_t)x * t.Kx + b] * __ldg(orow + t.idx_x[(size_t)x * t.Kx + b]);
         acc += t.w_y[(size_t)y * t.Ky + a] * r;
     }
-    dfm[i] = acc;
+    dfm[(size_t)row * g.W + x] = acc;
 }
 
 ResizeGeom make_geom(int C, int H, int W, int Hg, int Wg) {
@@ -180,8 +180,15 @@ cudaError_t launch_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const
                                                       const_cast<float*>(t.w_y));
     resize_tables_kernel<<<(W + 127) / 128, 128, 0, s>>>(W, Wg, g.rx, Kx, const_cast<int*>(t.cnt_x), const_cast<int*>(t.idx_x),
                                                       const_cast<float*>(t.w_x));
-    resize_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, t, dout, dfm);
-    g_launches += 3;
+    // gridDim.y <= 65535: rows are processed in slabs
+    const int rows = C * H;
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = std::min(65535, rows - r0);
+        ResizeGeom gs = g;
+        // a slab starts at row r0: shift the base pointers by whole rows; (c, y) are recovered from r0 + blockIdx.y
+        resize_bwd_kernel<<<dim3((W + 255) / 256, nr), 256, 0, s>>>(gs, t, dout, dfm + 0, r0);
+    }
+    g_launches += 2 + (rows + 65534) / 65535;
     e = cudaGetLastError();
     cudaFreeAsync(ws, s);
     return e;
