@@ -116,25 +116,66 @@ struct GatherTables {
     int Ky, Kx;
 };
 
-// grid = (ceil(W / 256), C * H): one block per 256-pixel piece of one gradient row, so the row's y-table entries are
-// block-uniform and nothing is divided per element (a flat 64-bit index with % W, % H cost 2.0 ms at config 3 -- more than
-// the composite it follows; this form is bound by the 1 GB it writes)
+// grid = (ceil(W / 1024), ceil(C * H / kRowsPerBlock)): a thread owns four consecutive pixels (one 128-bit store) of
+// kRowsPerBlock consecutive gradient rows, its x-table entries stay in registers across the rows, the rows' y-table entries
+// are block-uniform, and nothing is divided per element.  (History: a flat 64-bit index with % W, % H per element took
+// 2.0 ms at config 3; one element per thread in 524 K tiny blocks was block-dispatch bound at 1.4 ms; this form streams.)
+constexpr int kRowsPerBlock = 8;   // at least; more when C * H / 8 would exceed the 65535 limit of gridDim.y
+constexpr int kMaxKx = 6;   // x-table entries kept in registers; wider tables (strong up-sampling) take the generic loop
+
 __global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, GatherTables t, const float* __restrict__ dout,
-                                                         float* __restrict__ dfm, int row0) {
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    const int row = row0 + blockIdx.y;   // c * H + y
-    const int c = row / g.H, y = row - c * g.H;
-    if (x >= g.W) return;
-    const float* p = dout + (size_t)c * g.Hg * g.Wg;
-    const int ny = t.cnt_y[y], nx = t.cnt_x[x];
-    float acc = 0.f;
-    for (int a = 0; a < ny; a++) {
-        const float* orow = p + (size_t)t.idx_y[(size_t)y * t.Ky + a] * g.Wg;
-        float r = 0.f;
-        for (int b = 0; b < nx; b++) r += t.w_x[(size_t)x * t.Kx + b] * __ldg(orow + t.idx_x[(size_t)x * t.Kx + b]);
-        acc += t.w_y[(size_t)y * t.Ky + a] * r;
+                                                         float* __restrict__ dfm, int rows_per_block) {
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x0 >= g.W) return;
+    const int rows = g.C * g.H;
+    int nx[4], ix[4][kMaxKx];
+    float wx[4][kMaxKx];
+    const bool small = t.Kx <= kMaxKx;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = x0 + j;
+        nx[j] = x < g.W ? t.cnt_x[x] : 0;
+        if (small) {
+#pragma unroll
+            for (int b = 0; b < kMaxKx; b++) {
+                const bool on = b < nx[j];
+                ix[j][b] = on ? t.idx_x[(size_t)x * t.Kx + b] : 0;
+                wx[j][b] = on ? t.w_x[(size_t)x * t.Kx + b] : 0.f;
+            }
+        }
     }
-    dfm[(size_t)row * g.W + x] = acc;
+    for (int r = 0; r < rows_per_block; r++) {
+        const int row = blockIdx.y * rows_per_block + r;  // c * H + y
+        if (row >= rows) break;
+        const int c = row / g.H, y = row - c * g.H;
+        const float* p = dout + (size_t)c * g.Hg * g.Wg;
+        const int ny = t.cnt_y[y];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int a = 0; a < ny; a++) {
+            const float* orow = p + (size_t)t.idx_y[(size_t)y * t.Ky + a] * g.Wg;
+            const float wy = t.w_y[(size_t)y * t.Ky + a];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float s = 0.f;
+                if (small) {
+#pragma unroll
+                    for (int b = 0; b < kMaxKx; b++) s += wx[j][b] * __ldg(orow + ix[j][b]);  // padded entries: weight 0, index 0
+                } else {
+                    const int x = x0 + j;
+                    for (int b = 0; b < nx[j]; b++) s += t.w_x[(size_t)x * t.Kx + b] * __ldg(orow + t.idx_x[(size_t)x * t.Kx + b]);
+                }
+                acc[j] += wy * s;
+            }
+        }
+        float* o = dfm + (size_t)row * g.W + x0;
+        if (x0 + 3 < g.W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (x0 + j < g.W) o[j] = acc[j];
+        }
+    }
 }
 
 ResizeGeom make_geom(int C, int H, int W, int Hg, int Wg) {
@@ -180,15 +221,10 @@ cudaError_t launch_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const
                                                       const_cast<float*>(t.w_y));
     resize_tables_kernel<<<(W + 127) / 128, 128, 0, s>>>(W, Wg, g.rx, Kx, const_cast<int*>(t.cnt_x), const_cast<int*>(t.idx_x),
                                                       const_cast<float*>(t.w_x));
-    // gridDim.y <= 65535: rows are processed in slabs
     const int rows = C * H;
-    for (int r0 = 0; r0 < rows; r0 += 65535) {
-        const int nr = std::min(65535, rows - r0);
-        ResizeGeom gs = g;
-        // a slab starts at row r0: shift the base pointers by whole rows; (c, y) are recovered from r0 + blockIdx.y
-        resize_bwd_kernel<<<dim3((W + 255) / 256, nr), 256, 0, s>>>(gs, t, dout, dfm + 0, r0);
-    }
-    g_launches += 2 + (rows + 65534) / 65535;
+    const int rpb = std::max(kRowsPerBlock, (rows + 65534) / 65535);
+    resize_bwd_kernel<<<dim3((W + 1023) / 1024, (rows + rpb - 1) / rpb), 256, 0, s>>>(g, t, dout, dfm, rpb);
+    g_launches += 3;
     e = cudaGetLastError();
     cudaFreeAsync(ws, s);
     return e;
