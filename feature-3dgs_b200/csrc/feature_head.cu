@@ -131,10 +131,12 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, GatherTab
     int nx[4], ix[4][kMaxKx];
     float wx[4][kMaxKx];
     const bool small = t.Kx <= kMaxKx;
+    int nmax = 0;  // entries actually present for this thread's four pixels (<= 2 when down-sampling)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int x = x0 + j;
         nx[j] = x < g.W ? t.cnt_x[x] : 0;
+        nmax = max(nmax, nx[j]);
         if (small) {
 #pragma unroll
             for (int b = 0; b < kMaxKx; b++) {
@@ -159,7 +161,8 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, GatherTab
                 float s = 0.f;
                 if (small) {
 #pragma unroll
-                    for (int b = 0; b < kMaxKx; b++) s += wx[j][b] * __ldg(orow + ix[j][b]);  // padded entries: weight 0, index 0
+                    for (int b = 0; b < kMaxKx; b++)
+                        if (b < nmax) s += wx[j][b] * __ldg(orow + ix[j][b]);  // padded entries: weight 0, index 0
                 } else {
                     const int x = x0 + j;
                     for (int b = 0; b < nx[j]; b++) s += t.w_x[(size_t)x * t.Kx + b] * __ldg(orow + t.idx_x[(size_t)x * t.Kx + b]);
