@@ -142,7 +142,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=list(scenegen.CONFIGS))
-    ap.add_argument("--views-per-rank", type=int, default=4)
+    ap.add_argument("--views-per-rank", type=int, default=8,
+                    help="views each rank renders per step (weak scaling; 8 x 8 GPUs = the 64-view batch of BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--api", default="batch", choices=["batch", "autograd"],
                     help="ours only: 'batch' = ViewBatch (autograd-free forward + in-kernel gradient accumulation, the "
