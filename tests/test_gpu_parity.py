@@ -446,3 +446,26 @@ def test_view_batch_accumulates_like_autograd(name):
         assert r <= 1.0, (k, r)
     assert torch.equal(vb.denom, denom)
     assert parity.float_mismatch(vb.grad_accum.cpu().numpy(), accum.cpu().numpy(), atol_rel=parity.GRAD_ATOL_REL)[0] <= 1.0
+
+
+# ------------------------------------------------------------------------------------------- per-process overrides
+@pytest.mark.parametrize("env", [{"F3DGS_TC": "0"}, {"F3DGS_BWD2": "0"}, {"F3DGS_TC": "0", "F3DGS_BWD2": "0"},
+                                 {"F3DGS_TC_MIN_C": "16"}])
+def test_kernel_selection_overrides_keep_parity(env):
+    """F3DGS_TC / F3DGS_BWD2 / F3DGS_TC_MIN_C are read once per process, so each setting runs in its own interpreter:
+    the fp32-pipe forward, the fused single-kernel backward and the tensor-core path at narrow widths must all pass the same
+    parity checks as the defaults."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import scenegen, parity\n"
+        "from test_gpu_parity import _check\n"
+        "for name in ('small', 'small128', 'small200'):\n"
+        "    sc = scenegen.make_config(name); _check(sc, sc.cameras[0], vs_ref=(name == 'small'))\n"
+        "print('OVERRIDE OK')\n" % (root, os.path.join(root, "feature-3dgs_b200"), os.path.join(root, "tests")))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OVERRIDE OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
