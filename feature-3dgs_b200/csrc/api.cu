@@ -311,8 +311,16 @@ int f3dgs_forward(f3dgs_alloc_fn geometry_alloc, void* geometry_ctx, f3dgs_alloc
     }
     STAGE_CHECK("scan");
 
-    static thread_local int* h_count = nullptr;
-    if (!h_count) CUDA_TRY(cudaHostAlloc((void**)&h_count, sizeof(int), cudaHostAllocDefault));
+    // one pinned word per calling thread for the 4-byte read-back; released when the thread ends
+    struct PinnedInt {
+        int* p = nullptr;
+        ~PinnedInt() {
+            if (p) cudaFreeHost(p);
+        }
+    };
+    static thread_local PinnedInt pinned;
+    if (!pinned.p) CUDA_TRY(cudaHostAlloc((void**)&pinned.p, sizeof(int), cudaHostAllocDefault));
+    int* h_count = pinned.p;
     CUDA_TRY(cudaMemcpyAsync(h_count, offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     const int R = *h_count;

@@ -591,26 +591,25 @@ composite_bwd_kernel(const BwdArgs args) {
     }
 }
 
-int composite_layout_bpa(int default_bpa);  // composite_fwd.cu
 
 template <int CH, int BPA>
 static cudaError_t launch_bwd_t(const ViewParams& vp, BwdArgs a, cudaStream_t s) {
     const size_t smem = sizeof(BwdSmem);
     // the opt-in to > 48 KB of dynamic shared memory is per device (context): remember it per device ordinal, so that one
     // process driving several GPUs works too
-    static int sms_of_device[64] = {0};
+    static std::atomic<int> sms_of_device[64];  // zero-initialised; set once per device (idempotent)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (sms_of_device[dev] == 0) {
+    if (sms_of_device[dev].load() == 0) {
         cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<CH, BPA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms_of_device[dev] = n > 0 ? n : 148;
+        sms_of_device[dev].store(n > 0 ? n : 148);
     }
-    const int num_sms = sms_of_device[dev];
+    const int num_sms = sms_of_device[dev].load();
     a.pa.chunks = CH > 0 ? (vp.C + CH - 1) / CH : 1;
     a.vec_io = 0;
     if (vp.W % 4 == 0 && (reinterpret_cast<uintptr_t>(a.dL_dfeat_pix) & 15) == 0) a.vec_io |= 1;
@@ -652,11 +651,11 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
     using SMEM = BwdSmemT<RingSlim>;
     const bool emit = list_w != nullptr;
     const size_t smem = sizeof(SMEM);
-    static int sms_of_device[64] = {0};
+    static std::atomic<int> sms_of_device[64];  // zero-initialised; set once per device (idempotent)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (sms_of_device[dev] == 0) {
+    if (sms_of_device[dev].load() == 0) {
         cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e == cudaSuccess)
@@ -665,7 +664,7 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
         if (e != cudaSuccess) return e;
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms_of_device[dev] = n > 0 ? n : 148;
+        sms_of_device[dev].store(n > 0 ? n : 148);
     }
     BwdArgs a;
     a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec; a.pa.features = nullptr;
@@ -678,7 +677,7 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
     a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    const int grid = min(a.pa.num_tiles, kSlimCtas * sms_of_device[dev]);
+    const int grid = min(a.pa.num_tiles, kSlimCtas * sms_of_device[dev].load());
     if (emit)
         composite_bwd_kernel<0, 1, true, true><<<grid, (kAlphaWarp0 + Layout<1>::kAlphaWarps) * 32, smem, s>>>(a);
     else
@@ -687,8 +686,7 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
     return cudaGetLastError();
 }
 
-#define F3DGS_BWD_DISPATCH(CHV) \
-    (composite_layout_bpa(1) == 2 ? launch_bwd_t<CHV, 2>(vp, a, s) : launch_bwd_t<CHV, 1>(vp, a, s))
+#define F3DGS_BWD_DISPATCH(CHV) launch_bwd_t<CHV, 1>(vp, a, s)
 
 cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                  const SplatRec* rec, const float* bg, const float* final_T,

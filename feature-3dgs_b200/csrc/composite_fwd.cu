@@ -44,7 +44,7 @@ namespace f3dgs {
 #define F3DGS_PAIR_SKIP 1      // 1 (with F3DGS_FFMA2): skip the FFMA2 group of a quad row whose two pixels did not blend
 #endif
 #ifndef F3DGS_FEAT_PREFETCH
-#define F3DGS_FEAT_PREFETCH 0  // 1: software-pipeline the sparse feature loop by one instance (mask + feature float4)
+#define F3DGS_FEAT_PREFETCH 1  // 1: software-pipeline the sparse feature loop by one instance (mask + feature float4)
 #endif
 static constexpr bool kTiming = F3DGS_TIMING_BUILD != 0;
 #define TICK() ((kTiming && args.dbg) ? clock64() : 0ll)
@@ -592,19 +592,8 @@ composite_fwd_kernel(const FwdArgs args) {
     }
 }
 
-// Warp layout per kernel (see Layout<> in composite_common.cuh).  Measured at c3 on B200 (round 1, final kernels):
-// forward 2.19 ms with 8 alpha warps x 1 block vs 2.41 ms with 4 alpha warps x 2 blocks (184-register feature
-// warps running the dense hoisted loop); backward 4.2 ms vs 5.5 ms.  Both default to 8 x 1.
-// F3DGS_BPA=1|2 overrides both for experiments.
-int composite_layout_bpa(int default_bpa) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("F3DGS_BPA");
-        forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
-    }
-    return forced ? forced : default_bpa;
-}
-
+// Warp layout (see Layout<> in composite_common.cuh): 8 alpha warps x 1 block (BPA = 1).  The 4 x 2 layout measured slower
+// at c3 in round 1 (forward 2.41 vs 2.19 ms, backward 5.5 vs 4.2 ms) and is no longer instantiated.
 template <int CH, int BPA>
 static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                 const SplatRec* rec, const float* features, const float* bg, float* final_T,
@@ -613,19 +602,19 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     const size_t smem = sizeof(RingV2<CH>);
     // the opt-in to > 48 KB of dynamic shared memory is per device (context): remember it per device ordinal, so that one
     // process driving several GPUs works too
-    static int sms_of_device[64] = {0};
+    static std::atomic<int> sms_of_device[64];  // zero-initialised; set once per device (idempotent)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (sms_of_device[dev] == 0) {
+    if (sms_of_device[dev].load() == 0) {
         cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<CH, BPA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms_of_device[dev] = n > 0 ? n : 148;
+        sms_of_device[dev].store(n > 0 ? n : 148);
     }
-    const int num_sms = sms_of_device[dev];
+    const int num_sms = sms_of_device[dev].load();
     FwdArgs a;
     a.pa.ranges = ranges; a.pa.point_list = point_list; a.pa.rec = rec;
     a.pa.features = CH > 0 ? features : nullptr;
@@ -668,12 +657,9 @@ static cudaError_t launch_fwd_t(const ViewParams& vp, const uint2* ranges, const
     return cudaGetLastError();
 }
 
-#define F3DGS_FWD_DISPATCH(CHV)                                                                                   \
-    (composite_layout_bpa(1) == 2                                                                                \
-         ? launch_fwd_t<CHV, 2>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,       \
-                                out_feature, out_depth, work_counter, s)                                        \
-         : launch_fwd_t<CHV, 1>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color,       \
-                                out_feature, out_depth, work_counter, s))
+#define F3DGS_FWD_DISPATCH(CHV)                                                                              \
+    launch_fwd_t<CHV, 1>(vp, ranges, point_list, rec, features, bg, final_T, n_contrib, out_color, out_feature, \
+                         out_depth, work_counter, s)
 
 cudaError_t launch_composite_fwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,
                                  const SplatRec* rec, const float* features, const float* bg,

@@ -208,16 +208,16 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 3) feature_bwd_kernel(const F
 
 // ------------------------------------------------------------------------------------------------ launchers
 static int workers_grid() {
-    static int sms_of_device[64] = {0};
+    static std::atomic<int> sms_of_device[64];  // zero-initialised; set once per device (idempotent)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return 148 * 3;
-    if (sms_of_device[dev] == 0) {
+    if (sms_of_device[dev].load() == 0) {
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms_of_device[dev] = n > 0 ? n : 148;
+        sms_of_device[dev].store(n > 0 ? n : 148);
     }
-    return sms_of_device[dev] * 3;  // __launch_bounds__(128, 3): three CTAs of four workers per SM
+    return sms_of_device[dev].load() * 3;  // __launch_bounds__(128, 3): three CTAs of four workers per SM
 }
 
 template <int CH>

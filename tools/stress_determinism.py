@@ -35,5 +35,5 @@ for it in range(runs):
         b = gbase[k].double(); tol = parity.RTOL * b.abs() + parity.GRAD_ATOL_REL * b.abs().max()
         v = float(((g[k].double() - b).abs() / tol).max()); worst = max(worst, v)
         if v > 0.5: print("run", it, "grad", k, "viol", v, flush=True)
-print(f"stress {name} BPA {os.environ.get('F3DGS_BPA','default')}: {runs} runs, forward mismatches {bad_fwd}, worst grad viol {worst:.4f}")
+print(f"stress {name}: {runs} runs, forward mismatches {bad_fwd}, worst grad viol {worst:.4f}")
 sys.exit(1 if bad_fwd or worst > 0.5 else 0)
