@@ -17,7 +17,12 @@
 
 namespace f3dgs {
 
-constexpr int kListChunk = 8;   // list entries staged per pipeline step
+// (An L2 prefetch of the next chunk's gradient rows ahead of their reductions was measured and lost: 3.06 vs 2.96 ms for the
+// whole backward at config 3, profiles/r02_fwd_tc_diag.txt.)
+#ifndef F3DGS_LIST_CHUNK
+#define F3DGS_LIST_CHUNK 16   // 16: 2.94 ms, 8: 2.96 ms for the whole backward at config 3
+#endif
+constexpr int kListChunk = F3DGS_LIST_CHUNK;   // list entries staged per pipeline step (<= 32)
 constexpr int kFeatWarps = 4;   // independent worker warps per CTA
 
 template <int CH, bool WITH_ROWS>
