@@ -1,4 +1,5 @@
 #!/bin/bash
+# final check of a round: full GPU suite, smoke, default bench line (ours + a short reference-arm run)
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
 timeout -s KILL 420 python -c "import torch; torch.zeros(8, device='cuda').sum().item()"
@@ -11,3 +12,4 @@ print('value',b['value'],'ms/step',b['ms_per_step'],'e2e',b['e2e'],'launches',b[
 print(b['roofline']['stage_ms_per_launch'], b['roofline']['frac'], b['roofline']['traffic'])
 PY
 tail -2 $O/r2p_bench_c3.err
+timeout -s KILL 400 python bench.py --impl reference --steps 2 --warmup 3 --no-cpu-baseline > $O/r2p_ref_c3.json 2> $O/r2p_ref_c3.err; cut -c1-300 $O/r2p_ref_c3.json; tail -2 $O/r2p_ref_c3.err
