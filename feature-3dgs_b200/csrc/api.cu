@@ -18,6 +18,9 @@
 #include "../../include/f3dgs_b200.h"
 #include "kernels.h"
 
+#ifndef F3DGS_FBWD_TC_DEFAULT
+#define F3DGS_FBWD_TC_DEFAULT 0
+#endif
 #ifndef F3DGS_BWD2_DEFAULT
 #define F3DGS_BWD2_DEFAULT 1
 #endif
@@ -155,6 +158,17 @@ inline bool tc_mode(int C, const float* features) {
         min_c = e ? atoi(e) : 33;  // measured: C = 64 (c5, c3 at C = 64) 32% faster on the tensor cores, C = 16 slightly slower
     }
     return on && C >= min_c && C % 4 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0;
+}
+
+// Feature gradient of the two-kernel backward on the tensor cores (feature_bwd.cu: feature_bwd_tc_kernel).
+// F3DGS_FBWD_TC=0|1 overrides the default per process.
+inline bool fbwd_tc_mode(int C) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("F3DGS_FBWD_TC");
+        on = e ? (e[0] == '1' ? 1 : 0) : F3DGS_FBWD_TC_DEFAULT;
+    }
+    return on && C > 32 && C % 4 == 0;
 }
 
 inline int bit_length(uint32_t n) {
@@ -472,7 +486,7 @@ int backward_impl(const char* who, bool accumulate, int P, int D, int M, int R, 
                 e = launch_feature_bwd(vp, ranges, reinterpret_cast<const float*>(lists + ll.w),
                                        reinterpret_cast<const uint2*>(lists + ll.meta),
                                        reinterpret_cast<const uint32_t*>(lists + ll.cnt), dL_dfeaturepix,
-                                       dL_dsemantic_feature, counters + 48, stream);
+                                       dL_dsemantic_feature, counters + 48, stream, fbwd_tc_mode(C));
             if (lists) cudaFreeAsync(lists, stream);
         } else {
             e = launch_composite_bwd(vp, ranges, point_list, rec, background, final_T, n_contrib, dL_dpix,

@@ -14,6 +14,7 @@
 // every 128-channel chunk (the alpha evaluation is not repeated per chunk).
 // Reference semantics: backward.cu:565-575 (feature gradient; the feature loss does not feed dL/dalpha, :575 disabled).
 #include "composite_common.cuh"
+#include "tc_common.cuh"
 
 namespace f3dgs {
 
@@ -211,6 +212,256 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 3) feature_bwd_kernel(const F
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core variant
+// The same lists, with the per-block contraction on the tensor cores:  D[entry, ch] = sum_px W[entry, px] * dO[ch, px]
+// is, per (tile, block, 128-channel chunk) and per 128 list entries, a GEMM with M = 128 entries, N = 128 channels,
+// K = 32 pixels -- four K = 8 steps of three tcgen05.mma each (3xTF32, tc_common.cuh): 12 MMAs of ~108 cycles
+// (profiles/r02_tc_rate.txt) per 128 entries, where the fp32 kernel above spends 128 x 64 FFMA2.  Both operands are K-major
+// SWIZZLE_128B ([row][32 floats], 16-byte chunk ^ (row & 7)): A = the list rows as they lie in memory (one row = the 32
+// weights of an entry), B = the block's upstream gradient transposed to [channel][pixel] in the list's pixel order.
+//
+// One CTA per SM, 16 warps: two LOADER groups of four warps, each owning one operand slot (fetch an item, stage B once per
+// item and A per 128 entries, hi / lo split on the way), one MMA issuer, four EPILOGUE warps (tcgen05.ld: lane = entry,
+// columns = channels; one red.global.add.v4 per lane and four channels into the entry's gradient row).  Slots hand over
+// with mbarriers: loader -> full -> MMA -> (tcgen05.commit) d_full -> epilogue -> d_empty -> loader.
+namespace {
+
+constexpr int kFbLoad0 = 4, kFbLoadWarpsPerGroup = 4, kFbGroups = 2;
+constexpr int kFbEpi0 = 12, kFbEpiN = 4, kFbMmaWarp = 1;
+constexpr int kFbThreads = (kFbEpi0 + kFbEpiN) * 32;
+constexpr int kFbRows = 128;  // list entries per MMA group
+constexpr int kFbTrStride = 132;  // floats; 16-byte aligned rows, conflict-free for lane = row STS.128 and lane = column LDS.128
+
+struct alignas(1024) FbSlot {
+    float Ahi[kFbRows][32];   // list rows (entries x 32 pixels), K-major SWIZZLE_128B
+    float Alo[kFbRows][32];
+    float Bhi[128][32];       // upstream gradient (channels x 32 pixels), K-major SWIZZLE_128B
+    float Blo[128][32];
+};
+static_assert(sizeof(FbSlot) == 64 * 1024, "operand slot is 64 KB");
+
+struct alignas(1024) FbSmem {
+    FbSlot slot[kFbGroups];
+    float tr[kFbEpiN][32][kFbTrStride];  // epilogue transpose: [entry][channel], so that one RED covers one entry's row
+    uint32_t gid[kFbGroups][kFbRows];
+    int32_t cnt[kFbGroups];     // rows of this hand-over; < 0: this group has no more work
+    int32_t ch0[kFbGroups];     // first channel of the chunk
+    int32_t item[kFbGroups];    // work item broadcast inside a loader group
+    uint64_t full[kFbGroups], d_full[kFbGroups], d_empty[kFbGroups];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void group_sync(int g) {  // named barrier 1 + g over the 128 threads of loader group g
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kFbLoadWarpsPerGroup * 32) : "memory");
+}
+
+__global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const FeatArgs a) {
+    extern __shared__ unsigned char fb_smem_dyn[];
+    FbSmem& sm = *reinterpret_cast<FbSmem*>(fb_smem_dyn + ((1024u - (smem_u32(fb_smem_dyn) & 1023u)) & 1023u));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int W = a.W, H = a.H, C = a.C;
+    const size_t HW = (size_t)H * W;
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < kFbGroups; g++) {
+            mbar_init(&sm.full[g], 1);
+            mbar_init(&sm.d_full[g], 1);
+            mbar_init(&sm.d_empty[g], kFbEpiN);
+        }
+        mbar_fence_init();
+    }
+    if (warp == kFbMmaWarp) tmem_alloc<256>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp >= kFbLoad0 && warp < kFbLoad0 + kFbGroups * kFbLoadWarpsPerGroup) {
+        // ==================================================================== loader groups
+        const int g = (warp - kFbLoad0) / kFbLoadWarpsPerGroup;
+        const int t = threadIdx.x - (kFbLoad0 + g * kFbLoadWarpsPerGroup) * 32;  // 0..127 inside the group
+        const int gw = t >> 5;
+        FbSlot& sl = sm.slot[g];
+        const int items = a.num_tiles * a.chunks * kBlocksPerTile;
+        uint32_t use = 0;
+        for (;;) {
+            if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);
+            group_sync(g);
+            const int item = sm.item[g];
+            group_sync(g);  // everyone has read it before the next overwrite
+            if (item >= items) break;
+            const ItemPos ip = decode_item(item, a);
+            const uint32_t rx = a.ranges[ip.tile].x, ry = a.ranges[ip.tile].y;
+            const size_t base = 8 * (size_t)rx + (size_t)ip.b * (ry - rx);
+            const uint32_t n = a.list_cnt[(size_t)ip.tile * kBlocksPerTile + ip.b];
+            if (n == 0) continue;
+            for (uint32_t e0 = 0; e0 < n; e0 += kFbRows, use++) {
+                const uint32_t cnt = min((uint32_t)kFbRows, n - e0);
+                mbar_wait_sleep(&sm.d_empty[g], (use & 1u) ^ 1u, 32);
+                if (e0 == 0) {
+                    // ---- B: this thread's channel, 32 pixels of the block, transposed into the list's pixel order
+                    const int ch = ip.chunk * 128 + t;
+                    float v[4][8];
+#pragma unroll
+                    for (int y = 0; y < 4; y++)
+#pragma unroll
+                        for (int x = 0; x < 8; x++) v[y][x] = 0.f;
+                    if (ch < C) {
+                        const float* plane = a.dL_dfeat_pix + (size_t)ch * HW;
+#pragma unroll
+                        for (int y = 0; y < 4; y++) {
+                            const int yy = ip.by0 + y;
+                            if (yy >= H) continue;
+                            if ((a.vec & 2) && ip.bx0 + 8 <= W) {
+                                const float4 p0 = ld_nc_f4(plane + (size_t)yy * W + ip.bx0);
+                                const float4 p1 = ld_nc_f4(plane + (size_t)yy * W + ip.bx0 + 4);
+                                v[y][0] = p0.x; v[y][1] = p0.y; v[y][2] = p0.z; v[y][3] = p0.w;
+                                v[y][4] = p1.x; v[y][5] = p1.y; v[y][6] = p1.z; v[y][7] = p1.w;
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < 8; x++)
+                                    if (ip.bx0 + x < W) v[y][x] = __ldg(plane + (size_t)yy * W + ip.bx0 + x);
+                            }
+                        }
+                    }
+                    // chunk j of the row = list lanes 4j .. 4j+3 = the 2x2 quad at (px0, py0) = ((j & 3) * 2, (j >> 2) * 2)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int px0 = (j & 3) * 2, py0 = (j >> 2) * 2;
+                        const float4 q = make_float4(v[py0][px0], v[py0][px0 + 1], v[py0 + 1][px0], v[py0 + 1][px0 + 1]);
+                        const float4 hi = make_float4(tf32_hi(q.x), tf32_hi(q.y), tf32_hi(q.z), tf32_hi(q.w));
+                        const float4 lo = make_float4(q.x - hi.x, q.y - hi.y, q.z - hi.z, q.w - hi.w);
+                        const int o = t * 32 + ((j ^ (t & 7)) << 2);
+                        *reinterpret_cast<float4*>(&sl.Bhi[0][0] + o) = hi;
+                        *reinterpret_cast<float4*>(&sl.Blo[0][0] + o) = lo;
+                    }
+                }
+                // ---- A: 128 list rows of 128 bytes; a warp instruction moves four rows (8 lanes x 16 bytes each)
+                const float* wsrc = a.list_w + (base + e0) * 32;
+#pragma unroll
+                for (int it = 0; it < kFbRows / 16; it++) {
+                    const int row = it * 16 + gw * 4 + (lane >> 3), c16 = lane & 7;
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < (int)cnt) q = __ldg(reinterpret_cast<const float4*>(wsrc + (size_t)row * 32) + c16);
+                    const float4 hi = make_float4(tf32_hi(q.x), tf32_hi(q.y), tf32_hi(q.z), tf32_hi(q.w));
+                    const float4 lo = make_float4(q.x - hi.x, q.y - hi.y, q.z - hi.z, q.w - hi.w);
+                    const int o = row * 32 + ((c16 ^ (row & 7)) << 2);
+                    *reinterpret_cast<float4*>(&sl.Ahi[0][0] + o) = hi;
+                    *reinterpret_cast<float4*>(&sl.Alo[0][0] + o) = lo;
+                }
+                if (t < (int)cnt) sm.gid[g][t] = __ldg(&a.list_meta[base + e0 + t]).x;
+                fence_async_smem();
+                group_sync(g);
+                if (t == 0) {
+                    sm.cnt[g] = (int)cnt;
+                    sm.ch0[g] = ip.chunk * 128;
+                    __threadfence_block();
+                    mbar_arrive(&sm.full[g]);
+                }
+            }
+        }
+        // no more work for this group: tell the MMA warp and (through it) the epilogue
+        mbar_wait_sleep(&sm.d_empty[g], (use & 1u) ^ 1u, 32);
+        if (t == 0) {
+            sm.cnt[g] = -1;
+            __threadfence_block();
+            mbar_arrive(&sm.full[g]);
+        }
+    } else if (warp == kFbMmaWarp) {
+        // ==================================================================== MMA issuer
+        constexpr uint32_t kIdesc = umma_idesc_tf32(128, 128, 0, 0);
+        uint32_t use[kFbGroups] = {0, 0}, alive = (1u << kFbGroups) - 1;
+        int g = 0;
+        while (alive) {
+            if (!((alive >> g) & 1u)) { g ^= 1; continue; }
+            mbar_wait(&sm.full[g], use[g] & 1u);
+            const int cnt = *reinterpret_cast<volatile int32_t*>(&sm.cnt[g]);
+            if (cnt < 0) {
+                alive &= ~(1u << g);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.d_full[g]);  // forwards the stop (cnt stays < 0)
+                use[g]++;
+                g ^= 1;
+                continue;
+            }
+            tc_fence_after();
+            if (lane == 0) {
+                const FbSlot& sl = sm.slot[g];
+                const uint32_t ah = smem_u32(&sl.Ahi[0][0]), al = smem_u32(&sl.Alo[0][0]);
+                const uint32_t bh = smem_u32(&sl.Bhi[0][0]), bl = smem_u32(&sl.Blo[0][0]);
+                const uint32_t d = tmem + (uint32_t)g * 128u;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {  // 8 pixels = 32 bytes inside the swizzled 128-byte rows
+                    const uint64_t a_hi = umma_desc(ah + k * 32, 16, 1024, kUmmaSw128), a_lo = umma_desc(al + k * 32, 16, 1024, kUmmaSw128);
+                    const uint64_t b_hi = umma_desc(bh + k * 32, 16, 1024, kUmmaSw128), b_lo = umma_desc(bl + k * 32, 16, 1024, kUmmaSw128);
+                    umma_tf32_ss(d, a_hi, b_hi, kIdesc, k == 0 ? 0u : 1u);
+                    umma_tf32_ss(d, a_hi, b_lo, kIdesc, 1u);
+                    umma_tf32_ss(d, a_lo, b_hi, kIdesc, 1u);
+                }
+                umma_commit(&sm.d_full[g]);
+            }
+            __syncwarp();
+            use[g]++;
+            g ^= 1;
+        }
+    } else if (warp >= kFbEpi0) {
+        // ==================================================================== epilogue warps
+        const int ew = warp - kFbEpi0;
+        uint32_t use[kFbGroups] = {0, 0}, alive = (1u << kFbGroups) - 1;
+        int g = 0;
+        while (alive) {
+            if (!((alive >> g) & 1u)) { g ^= 1; continue; }
+            mbar_wait_sleep(&sm.d_full[g], use[g] & 1u, 32);
+            tc_fence_after();
+            const int cnt = *reinterpret_cast<volatile int32_t*>(&sm.cnt[g]);
+            if (cnt < 0) {
+                alive &= ~(1u << g);
+                use[g]++;
+                g ^= 1;
+                continue;
+            }
+            const int ch0 = *reinterpret_cast<volatile int32_t*>(&sm.ch0[g]);
+            const int rows = min(32, cnt - 32 * ew);  // this warp's quarter of the accumulator: entries 32 ew .. 32 ew + 31
+            float(*tr)[kFbTrStride] = sm.tr[ew];
+            if (rows > 0) {
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem + ((uint32_t)(32 * ew) << 16) + (uint32_t)(g * 128 + j * 32), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        *reinterpret_cast<float4*>(&tr[lane][j * 32 + q * 4]) =
+                            make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                        __uint_as_float(r[4 * q + 3]));
+                }
+            }
+            const uint32_t my_gid = lane < rows ? sm.gid[g][32 * ew + lane] : 0u;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.d_empty[g]);  // accumulator and ids are out: the slot can be refilled
+            const bool col_ok = ch0 + lane * 4 < C;  // C % 4 == 0 on this path
+            float* dst = a.dL_dfeature + ch0 + lane * 4;
+            for (int r = 0; r < rows; r++) {
+                const uint32_t gid = __shfl_sync(0xffffffffu, my_gid, r);
+                if (col_ok) red_add_f4(dst + (size_t)gid * C, *reinterpret_cast<const float4*>(&tr[r][lane * 4]));
+            }
+            __syncwarp();
+            use[g]++;
+            g ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kFbMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem);
+    }
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------ launchers
 static int workers_grid() {
     static std::atomic<int> sms_of_device[64];  // zero-initialised; set once per device (idempotent)
@@ -239,7 +490,7 @@ static int feat_ch(int C) { return C <= 32 ? 32 : (C <= 64 ? 64 : 128); }
 
 cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const float* list_w, const uint2* list_meta,
                                const uint32_t* list_cnt, const float* dL_dfeat_pix, float* dL_dfeature,
-                               int* work_counter, cudaStream_t s) {
+                               int* work_counter, cudaStream_t s, bool use_tc) {
     FeatArgs a;
     a.ranges = ranges; a.list_w = list_w; a.list_meta = list_meta; a.list_cnt = list_cnt;
     a.dL_dfeat_pix = dL_dfeat_pix; a.dL_dfeature = dL_dfeature;
@@ -252,6 +503,25 @@ cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const 
     if (vp.W % 4 == 0 && (reinterpret_cast<uintptr_t>(dL_dfeat_pix) & 15) == 0) a.vec |= 2;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
+    if (use_tc && (a.vec & 1)) {
+        a.chunks = (vp.C + 127) / 128;
+        const size_t smem = sizeof(FbSmem) + 1024;
+        static std::atomic<int> sms_of_device[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        if (sms_of_device[dev].load() == 0) {
+            e = cudaFuncSetAttribute(feature_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int n = 0;
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            sms_of_device[dev].store(n > 0 ? n : 148);
+        }
+        const int items = a.num_tiles * a.chunks * kBlocksPerTile;
+        feature_bwd_tc_kernel<<<min(items, sms_of_device[dev].load()), kFbThreads, smem, s>>>(a);
+        g_launches++;
+        return cudaGetLastError();
+    }
     if (CH == 32) return launch_feat_bwd_t<32>(a, s);
     if (CH == 64) return launch_feat_bwd_t<64>(a, s);
     return launch_feat_bwd_t<128>(a, s);

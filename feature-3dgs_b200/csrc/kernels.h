@@ -71,7 +71,7 @@ cudaError_t launch_composite_bwd_geom_slim(const ViewParams& vp, const uint2* ra
 // ---- feature_bwd.cu: feature gradient from the instance lists (second kernel of the two-kernel backward)
 cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const float* list_w, const uint2* list_meta,
                                const uint32_t* list_cnt, const float* dL_dfeat_pix, float* dL_dfeature,
-                               int* work_counter, cudaStream_t s);
+                               int* work_counter, cudaStream_t s, bool use_tc = false);
 
 // ---- composite_bwd.cu
 cudaError_t launch_composite_bwd(const ViewParams& vp, const uint2* ranges, const uint32_t* point_list,

@@ -131,6 +131,9 @@ def main():
             os.environ["F3DGS_TC"] = "1"  # tensor-core feature contraction (read once per library instance)
         if "+notc" in name:
             os.environ["F3DGS_TC"] = "0"
+        os.environ.pop("F3DGS_FBWD_TC", None)
+        if "+fbtc" in name:
+            os.environ["F3DGS_FBWD_TC"] = "1"  # tensor-core feature-gradient kernel
         os.environ.pop("F3DGS_BWD2", None)
         if "+bwd1" in name:
             os.environ["F3DGS_BWD2"] = "0"  # fused single-kernel backward
