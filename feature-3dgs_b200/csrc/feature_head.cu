@@ -38,43 +38,53 @@ __device__ __forceinline__ void src_of(int o, float r, int in, int& i0, int& i1,
     l0 = 1.0f - l1;
 }
 
-// grid-stride over the elements of the [C, Hg, Wg] output, x fastest; a persistent grid (a few CTAs per SM) so that the
-// loss needs one atomic per CTA, not one per 256 elements (200 K same-address atomics cost more than the whole resize)
-__global__ void __launch_bounds__(256) resize_fwd_kernel(ResizeGeom g, const float* __restrict__ fm,
-                                                         const float* __restrict__ gt, float grad_scale,
-                                                         float* __restrict__ out, float* __restrict__ loss_sum) {
-    const size_t n = (size_t)g.C * g.Hg * g.Wg;
+// One warp per output row (c, oy) at a time, lanes strided over ox: the row's channel plane and y taps are computed once per
+// row (no per-element division), a lane's loads are independent across its elements, and consecutive lanes read source
+// columns (in - 1) / (out - 1) apart -- neighbouring sectors.  A persistent grid, so that the loss needs one atomic per CTA
+// (200 K same-address atomics cost more than the whole resize).
+constexpr int kFwdThreads = 256;
+
+__global__ void __launch_bounds__(kFwdThreads) resize_fwd_kernel(ResizeGeom g, const float* __restrict__ fm,
+                                                                 const float* __restrict__ gt, float grad_scale,
+                                                                 float* __restrict__ out, float* __restrict__ loss_sum) {
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (kFwdThreads / 32);
+    const int rows = g.C * g.Hg;
     float ad = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % g.Wg);
-        const int oy = (int)((i / g.Wg) % g.Hg);
-        const int c = (int)(i / ((size_t)g.Wg * g.Hg));
-        int y0, y1, x0, x1;
-        float ly0, ly1, lx0, lx1;
+    for (int row = blockIdx.x * (kFwdThreads / 32) + (threadIdx.x >> 5); row < rows; row += warps) {
+        const int c = row / g.Hg, oy = row - c * g.Hg;
+        int y0, y1;
+        float ly0, ly1;
         src_of(oy, g.ry, g.H, y0, y1, ly0, ly1);
-        src_of(ox, g.rx, g.W, x0, x1, lx0, lx1);
-        const float* p = fm + (size_t)c * g.H * g.W;
-        const float v = ly0 * (lx0 * __ldg(p + (size_t)y0 * g.W + x0) + lx1 * __ldg(p + (size_t)y0 * g.W + x1)) +
-                        ly1 * (lx0 * __ldg(p + (size_t)y1 * g.W + x0) + lx1 * __ldg(p + (size_t)y1 * g.W + x1));
-        if (gt != nullptr) {
-            const float d = v - gt[i];
-            ad += fabsf(d);
-            out[i] = d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f);
-        } else {
-            out[i] = v;
+        const float* p0 = fm + ((size_t)c * g.H + y0) * g.W;
+        const float* p1 = fm + ((size_t)c * g.H + y1) * g.W;
+        const size_t obase = (size_t)row * g.Wg;
+#pragma unroll 2
+        for (int ox = lane; ox < g.Wg; ox += 32) {
+            int x0, x1;
+            float lx0, lx1;
+            src_of(ox, g.rx, g.W, x0, x1, lx0, lx1);
+            const float v = ly0 * (lx0 * __ldg(p0 + x0) + lx1 * __ldg(p0 + x1)) + ly1 * (lx0 * __ldg(p1 + x0) + lx1 * __ldg(p1 + x1));
+            if (gt != nullptr) {
+                const float d = v - __ldg(gt + obase + ox);
+                ad += fabsf(d);
+                out[obase + ox] = d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f);
+            } else {
+                out[obase + ox] = v;
+            }
         }
     }
     if (gt != nullptr && loss_sum != nullptr) {
         // block reduction of |d|, one atomic per block
-        __shared__ float part[8];
+        __shared__ float part[kFwdThreads / 32];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ad += __shfl_xor_sync(0xffffffffu, ad, o);
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ad;
+        if (lane == 0) part[threadIdx.x >> 5] = ad;
         __syncthreads();
-        if (threadIdx.x < 8) {
+        if (threadIdx.x < kFwdThreads / 32) {
             float s = part[threadIdx.x];
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+            for (int o = kFwdThreads / 64; o > 0; o >>= 1) s += __shfl_xor_sync((1u << (kFwdThreads / 32)) - 1u, s, o);
             if (threadIdx.x == 0) atomicAdd(loss_sum, s);
         }
     }
@@ -181,6 +191,65 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(ResizeGeom g, GatherTab
     }
 }
 
+// Down-sampling by more than 2 (the reference's 1/2.25 teacher maps): consecutive outputs sample source positions more than
+// two apart, so every source pixel has AT MOST ONE output per axis and the gather is a single product.  A block owns
+// rows_per_block gradient rows (their y entries staged once in shared memory) and 4 x blockDim columns; a thread's four
+// pixels are blockDim apart, so every load and store instruction of a warp covers 128 contiguous bytes whatever W's
+// alignment is, and the four rows of a trip are independent loads in flight.
+constexpr int kOneMaxRows = 32;
+
+__global__ void __launch_bounds__(512) resize_bwd_one_kernel(ResizeGeom g, GatherTables t, const float* __restrict__ dout,
+                                                             float* __restrict__ dfm, int rows_per_block) {
+    __shared__ size_t s_off[kOneMaxRows];
+    __shared__ float s_wy[kOneMaxRows];
+    const int rows = g.C * g.H, row0 = blockIdx.y * rows_per_block, T = blockDim.x;
+    if ((int)threadIdx.x < rows_per_block) {
+        const int row = row0 + threadIdx.x;
+        size_t off = 0;
+        float wy = 0.f;
+        if (row < rows) {
+            const int c = row / g.H, y = row - c * g.H;
+            const bool on = t.cnt_y[y] > 0;
+            wy = on ? t.w_y[(size_t)y * t.Ky] : 0.f;
+            off = ((size_t)c * g.Hg + (on ? t.idx_y[(size_t)y * t.Ky] : 0)) * g.Wg;
+        }
+        s_off[threadIdx.x] = off;
+        s_wy[threadIdx.x] = wy;
+    }
+    __syncthreads();
+    int ix[4];
+    float wx[4];
+    bool in[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = (blockIdx.x * 4 + j) * T + threadIdx.x;
+        in[j] = x < g.W;
+        const bool on = in[j] && t.cnt_x[x] > 0;
+        ix[j] = on ? t.idx_x[(size_t)x * t.Kx] : 0;
+        wx[j] = on ? t.w_x[(size_t)x * t.Kx] : 0.f;
+    }
+    const int nrow = min(rows_per_block, rows - row0);
+    for (int r = 0; r < nrow; r += 4) {
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool live = r + u < nrow;
+            const float wy = live ? s_wy[r + u] : 0.f;
+            const float* orow = dout + (live ? s_off[r + u] : 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[u][j] = (wy != 0.f) ? wy * wx[j] * __ldg(orow + ix[j]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (r + u >= nrow) break;
+            float* o = dfm + (size_t)(row0 + r + u) * g.W + (size_t)blockIdx.x * 4 * T + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (in[j]) o[j * T] = v[u][j];
+        }
+    }
+}
+
 ResizeGeom make_geom(int C, int H, int W, int Hg, int Wg) {
     ResizeGeom g;
     g.C = C; g.H = H; g.W = W; g.Hg = Hg; g.Wg = Wg;
@@ -198,8 +267,10 @@ cudaError_t launch_feature_resize_fwd(int C, int H, int W, int Hg, int Wg, const
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sms * 8);
-    resize_fwd_kernel<<<grid, 256, 0, s>>>(make_geom(C, H, W, Hg, Wg), fm, gt, grad_scale, out, loss_sum);
+    const size_t rows = (size_t)C * Hg;
+    if (rows > 0x7fffffffu) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)std::min<size_t>((rows + kFwdThreads / 32 - 1) / (kFwdThreads / 32), (size_t)sms * 8);
+    resize_fwd_kernel<<<grid, kFwdThreads, 0, s>>>(make_geom(C, H, W, Hg, Wg), fm, gt, grad_scale, out, loss_sum);
     g_launches++;
     return cudaGetLastError();
 }
@@ -225,8 +296,14 @@ cudaError_t launch_feature_resize_bwd(int C, int H, int W, int Hg, int Wg, const
     resize_tables_kernel<<<(W + 127) / 128, 128, 0, s>>>(W, Wg, g.rx, Kx, const_cast<int*>(t.cnt_x), const_cast<int*>(t.idx_x),
                                                       const_cast<float*>(t.w_x));
     const int rows = C * H;
-    const int rpb = std::max(kRowsPerBlock, (rows + 65534) / 65535);
-    resize_bwd_kernel<<<dim3((W + 1023) / 1024, (rows + rpb - 1) / rpb), 256, 0, s>>>(g, t, dout, dfm, rpb);
+    if (g.ry >= 2.001f && g.rx >= 2.001f && (rows + kOneMaxRows - 1) / kOneMaxRows <= 65535) {
+        const int T = std::min(512, ((W + 3) / 4 + 31) / 32 * 32);
+        const int rpb = std::max(16, std::min(kOneMaxRows, (rows + 65534) / 65535));
+        resize_bwd_one_kernel<<<dim3((W + 4 * T - 1) / (4 * T), (rows + rpb - 1) / rpb), T, 0, s>>>(g, t, dout, dfm, rpb);
+    } else {
+        const int rpb = std::max(kRowsPerBlock, (rows + 65534) / 65535);
+        resize_bwd_kernel<<<dim3((W + 1023) / 1024, (rows + rpb - 1) / rpb), 256, 0, s>>>(g, t, dout, dfm, rpb);
+    }
     g_launches += 3;
     e = cudaGetLastError();
     cudaFreeAsync(ws, s);

@@ -102,7 +102,7 @@ def test_ply_and_feature_map_round_trip(tmp_path):
 
 # =================================================================================================== GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,size", SHAPES + [((128, 270, 480), (120, 160))])
+@pytest.mark.parametrize("shape,size", SHAPES + [((128, 270, 480), (120, 160)), ((3, 45, 2101), (20, 900))])
 def test_feature_head_kernels_match_pytorch_gpu(shape, size):
     from diff_gaussian_rasterization import feature_head as fh
 
