@@ -13,6 +13,8 @@
 // entry.  No inter-warp synchronisation at all; 12 warps per SM.  Channel counts above 128 reuse the same lists for
 // every 128-channel chunk (the alpha evaluation is not repeated per chunk).
 // Reference semantics: backward.cu:565-575 (feature gradient; the feature loss does not feed dL/dalpha, :575 disabled).
+#include <cstdlib>
+
 #include "composite_common.cuh"
 #include "tc_common.cuh"
 
@@ -220,14 +222,19 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 3) feature_bwd_kernel(const F
 // SWIZZLE_128B ([row][32 floats], 16-byte chunk ^ (row & 7)): A = the list rows as they lie in memory (one row = the 32
 // weights of an entry), B = the block's upstream gradient transposed to [channel][pixel] in the list's pixel order.
 //
-// One CTA per SM, 16 warps: two LOADER groups of four warps, each owning one operand slot (fetch an item, stage B once per
-// item and A per 128 entries, hi / lo split on the way), one MMA issuer, four EPILOGUE warps (tcgen05.ld: lane = entry,
-// columns = channels; one red.global.add.v4 per lane and four channels into the entry's gradient row).  Slots hand over
-// with mbarriers: loader -> full -> MMA -> (tcgen05.commit) d_full -> epilogue -> d_empty -> loader.
+// One CTA per SM, 16 warps:
+//   two LOADER groups of four warps, each owning one operand slot and one accumulator: fetch an item, stage B once per item
+//     and A per 128 entries (hi / lo split on the way, the A rows prefetched into registers before the slot is free), then
+//     the group's first thread issues the 12 MMAs and commits them to d_full;
+//   four EPILOGUE warps (tcgen05.ld: lane = entry, registers = channels) transpose their 32 entries through shared memory
+//     so that one red.global.add.v4 instruction covers one entry's 512-byte gradient row, release the accumulator
+//     (d_empty), and issue the REDs of the even rows;
+//   four HELPER warps issue the REDs of the odd rows (a warp's REDs go out one after the other: twice the warps, twice
+//     the REDs in flight).
 namespace {
 
-constexpr int kFbLoad0 = 4, kFbLoadWarpsPerGroup = 4, kFbGroups = 2;
-constexpr int kFbEpi0 = 12, kFbEpiN = 4, kFbMmaWarp = 1;
+constexpr int kFbHelp0 = 0, kFbLoad0 = 4, kFbLoadWarpsPerGroup = 4, kFbGroups = 2;
+constexpr int kFbEpi0 = 12, kFbEpiN = 4;
 constexpr int kFbThreads = (kFbEpi0 + kFbEpiN) * 32;
 constexpr int kFbRows = 128;  // list entries per MMA group
 constexpr int kFbTrStride = 132;  // floats; 16-byte aligned rows, conflict-free for lane = row STS.128 and lane = column LDS.128
@@ -243,19 +250,47 @@ static_assert(sizeof(FbSlot) == 64 * 1024, "operand slot is 64 KB");
 struct alignas(1024) FbSmem {
     FbSlot slot[kFbGroups];
     float tr[kFbEpiN][32][kFbTrStride];  // epilogue transpose: [entry][channel], so that one RED covers one entry's row
+    uint32_t tr_gid[kFbEpiN][32];
+    int32_t tr_rows[kFbEpiN];   // rows of tr[ew] to reduce; < 0: no more work (helper exits)
+    int32_t tr_ch0[kFbEpiN];
     uint32_t gid[kFbGroups][kFbRows];
     int32_t cnt[kFbGroups];     // rows of this hand-over; < 0: this group has no more work
     int32_t ch0[kFbGroups];     // first channel of the chunk
     int32_t item[kFbGroups];    // work item broadcast inside a loader group
-    uint64_t full[kFbGroups], d_full[kFbGroups], d_empty[kFbGroups];
+    uint64_t d_full[kFbGroups], d_empty[kFbGroups];
     uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void group_sync(int g) {  // named barrier 1 + g over the 128 threads of loader group g
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kFbLoadWarpsPerGroup * 32) : "memory");
 }
+__device__ __forceinline__ void pair_sync(int ew) {  // named barrier 3 + ew: epilogue warp ew and its helper
+    asm volatile("bar.sync %0, %1;" ::"r"(3 + ew), "r"(64) : "memory");
+}
 
-__global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const FeatArgs a) {
+// REDs of rows first, first + step, ... of one transposed quarter
+__device__ __forceinline__ void fb_reduce_rows(const FbSmem& sm, int ew, int lane, int first, int step, int rows, int ch0,
+                                               const FeatArgs& a) {
+    const bool col_ok = ch0 + lane * 4 < a.C;  // C % 4 == 0 on this path
+    if (!col_ok) return;
+    float* dst = a.dL_dfeature + ch0 + lane * 4;
+    int r = first;
+    for (; r + 3 * step < rows; r += 4 * step) {
+        float4 v[4];
+        uint32_t gid[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            gid[u] = sm.tr_gid[ew][r + u * step];
+            v[u] = *reinterpret_cast<const float4*>(&sm.tr[ew][r + u * step][lane * 4]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) red_add_f4(dst + (size_t)gid[u] * a.C, v[u]);
+    }
+    for (; r < rows; r += step)
+        red_add_f4(dst + (size_t)sm.tr_gid[ew][r] * a.C, *reinterpret_cast<const float4*>(&sm.tr[ew][r][lane * 4]));
+}
+
+__global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const FeatArgs a, const int helpers) {
     extern __shared__ unsigned char fb_smem_dyn[];
     FbSmem& sm = *reinterpret_cast<FbSmem*>(fb_smem_dyn + ((1024u - (smem_u32(fb_smem_dyn) & 1023u)) & 1023u));
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -264,13 +299,12 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
 
     if (threadIdx.x == 0) {
         for (int g = 0; g < kFbGroups; g++) {
-            mbar_init(&sm.full[g], 1);
             mbar_init(&sm.d_full[g], 1);
             mbar_init(&sm.d_empty[g], kFbEpiN);
         }
         mbar_fence_init();
     }
-    if (warp == kFbMmaWarp) tmem_alloc<256>(&sm.tmem_base);
+    if (warp == 0) tmem_alloc<256>(&sm.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -283,21 +317,42 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
         const int gw = t >> 5;
         FbSlot& sl = sm.slot[g];
         const int items = a.num_tiles * a.chunks * kBlocksPerTile;
+        constexpr uint32_t kIdesc = umma_idesc_tf32(128, 128, 0, 0);
         uint32_t use = 0;
-        for (;;) {
-            if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);
-            group_sync(g);
-            const int item = sm.item[g];
-            group_sync(g);  // everyone has read it before the next overwrite
-            if (item >= items) break;
+        if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);
+        group_sync(g);
+        int item = sm.item[g];
+        while (item < items) {
+            group_sync(g);  // everyone has read the index
+            if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);  // the next one arrives while this one is staged
             const ItemPos ip = decode_item(item, a);
             const uint32_t rx = a.ranges[ip.tile].x, ry = a.ranges[ip.tile].y;
             const size_t base = 8 * (size_t)rx + (size_t)ip.b * (ry - rx);
             const uint32_t n = a.list_cnt[(size_t)ip.tile * kBlocksPerTile + ip.b];
-            if (n == 0) continue;
             for (uint32_t e0 = 0; e0 < n; e0 += kFbRows, use++) {
                 const uint32_t cnt = min((uint32_t)kFbRows, n - e0);
+                // ---- A: 128 list rows of 128 bytes; a warp instruction moves four rows (8 lanes x 16 bytes each).  Loaded
+                // before the slot is free: the global latency overlaps the previous group's MMAs and accumulator read.
+                const float* wsrc = a.list_w + (base + e0) * 32;
+                float4 q[kFbRows / 16];
+#pragma unroll
+                for (int it = 0; it < kFbRows / 16; it++) {
+                    const int row = it * 16 + gw * 4 + (lane >> 3);
+                    q[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < (int)cnt) q[it] = __ldg(reinterpret_cast<const float4*>(wsrc + (size_t)row * 32) + (lane & 7));
+                }
+                const uint32_t my_gid = t < (int)cnt ? __ldg(&a.list_meta[base + e0 + t]).x : 0u;
                 mbar_wait_sleep(&sm.d_empty[g], (use & 1u) ^ 1u, 32);
+#pragma unroll
+                for (int it = 0; it < kFbRows / 16; it++) {
+                    const int row = it * 16 + gw * 4 + (lane >> 3), c16 = lane & 7;
+                    const float4 hi = make_float4(tf32_hi(q[it].x), tf32_hi(q[it].y), tf32_hi(q[it].z), tf32_hi(q[it].w));
+                    const float4 lo = make_float4(q[it].x - hi.x, q[it].y - hi.y, q[it].z - hi.z, q[it].w - hi.w);
+                    const int o = row * 32 + ((c16 ^ (row & 7)) << 2);
+                    *reinterpret_cast<float4*>(&sl.Ahi[0][0] + o) = hi;
+                    *reinterpret_cast<float4*>(&sl.Alo[0][0] + o) = lo;
+                }
+                sm.gid[g][t] = my_gid;
                 if (e0 == 0) {
                     // ---- B: this thread's channel, 32 pixels of the block, transposed into the list's pixel order
                     const int ch = ip.chunk * 128 + t;
@@ -328,81 +383,45 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int px0 = (j & 3) * 2, py0 = (j >> 2) * 2;
-                        const float4 q = make_float4(v[py0][px0], v[py0][px0 + 1], v[py0 + 1][px0], v[py0 + 1][px0 + 1]);
-                        const float4 hi = make_float4(tf32_hi(q.x), tf32_hi(q.y), tf32_hi(q.z), tf32_hi(q.w));
-                        const float4 lo = make_float4(q.x - hi.x, q.y - hi.y, q.z - hi.z, q.w - hi.w);
+                        const float4 p = make_float4(v[py0][px0], v[py0][px0 + 1], v[py0 + 1][px0], v[py0 + 1][px0 + 1]);
+                        const float4 hi = make_float4(tf32_hi(p.x), tf32_hi(p.y), tf32_hi(p.z), tf32_hi(p.w));
+                        const float4 lo = make_float4(p.x - hi.x, p.y - hi.y, p.z - hi.z, p.w - hi.w);
                         const int o = t * 32 + ((j ^ (t & 7)) << 2);
                         *reinterpret_cast<float4*>(&sl.Bhi[0][0] + o) = hi;
                         *reinterpret_cast<float4*>(&sl.Blo[0][0] + o) = lo;
                     }
                 }
-                // ---- A: 128 list rows of 128 bytes; a warp instruction moves four rows (8 lanes x 16 bytes each)
-                const float* wsrc = a.list_w + (base + e0) * 32;
-#pragma unroll
-                for (int it = 0; it < kFbRows / 16; it++) {
-                    const int row = it * 16 + gw * 4 + (lane >> 3), c16 = lane & 7;
-                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < (int)cnt) q = __ldg(reinterpret_cast<const float4*>(wsrc + (size_t)row * 32) + c16);
-                    const float4 hi = make_float4(tf32_hi(q.x), tf32_hi(q.y), tf32_hi(q.z), tf32_hi(q.w));
-                    const float4 lo = make_float4(q.x - hi.x, q.y - hi.y, q.z - hi.z, q.w - hi.w);
-                    const int o = row * 32 + ((c16 ^ (row & 7)) << 2);
-                    *reinterpret_cast<float4*>(&sl.Ahi[0][0] + o) = hi;
-                    *reinterpret_cast<float4*>(&sl.Alo[0][0] + o) = lo;
-                }
-                if (t < (int)cnt) sm.gid[g][t] = __ldg(&a.list_meta[base + e0 + t]).x;
-                fence_async_smem();
-                group_sync(g);
                 if (t == 0) {
                     sm.cnt[g] = (int)cnt;
                     sm.ch0[g] = ip.chunk * 128;
-                    __threadfence_block();
-                    mbar_arrive(&sm.full[g]);
+                }
+                fence_async_smem();
+                group_sync(g);
+                if (t == 0) {
+                    tc_fence_after();
+                    const uint32_t ah = smem_u32(&sl.Ahi[0][0]), al = smem_u32(&sl.Alo[0][0]);
+                    const uint32_t bh = smem_u32(&sl.Bhi[0][0]), bl = smem_u32(&sl.Blo[0][0]);
+                    const uint32_t d = tmem + (uint32_t)g * 128u;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {  // 8 pixels = 32 bytes inside the swizzled 128-byte rows
+                        const uint64_t a_hi = umma_desc(ah + k * 32, 16, 1024, kUmmaSw128), a_lo = umma_desc(al + k * 32, 16, 1024, kUmmaSw128);
+                        const uint64_t b_hi = umma_desc(bh + k * 32, 16, 1024, kUmmaSw128), b_lo = umma_desc(bl + k * 32, 16, 1024, kUmmaSw128);
+                        umma_tf32_ss(d, a_hi, b_hi, kIdesc, k == 0 ? 0u : 1u);
+                        umma_tf32_ss(d, a_hi, b_lo, kIdesc, 1u);
+                        umma_tf32_ss(d, a_lo, b_hi, kIdesc, 1u);
+                    }
+                    umma_commit(&sm.d_full[g]);
                 }
             }
+            group_sync(g);
+            item = sm.item[g];
         }
-        // no more work for this group: tell the MMA warp and (through it) the epilogue
+        // no more work for this group: tell the epilogue once the last accumulator has been read
         mbar_wait_sleep(&sm.d_empty[g], (use & 1u) ^ 1u, 32);
         if (t == 0) {
             sm.cnt[g] = -1;
             __threadfence_block();
-            mbar_arrive(&sm.full[g]);
-        }
-    } else if (warp == kFbMmaWarp) {
-        // ==================================================================== MMA issuer
-        constexpr uint32_t kIdesc = umma_idesc_tf32(128, 128, 0, 0);
-        uint32_t use[kFbGroups] = {0, 0}, alive = (1u << kFbGroups) - 1;
-        int g = 0;
-        while (alive) {
-            if (!((alive >> g) & 1u)) { g ^= 1; continue; }
-            mbar_wait(&sm.full[g], use[g] & 1u);
-            const int cnt = *reinterpret_cast<volatile int32_t*>(&sm.cnt[g]);
-            if (cnt < 0) {
-                alive &= ~(1u << g);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.d_full[g]);  // forwards the stop (cnt stays < 0)
-                use[g]++;
-                g ^= 1;
-                continue;
-            }
-            tc_fence_after();
-            if (lane == 0) {
-                const FbSlot& sl = sm.slot[g];
-                const uint32_t ah = smem_u32(&sl.Ahi[0][0]), al = smem_u32(&sl.Alo[0][0]);
-                const uint32_t bh = smem_u32(&sl.Bhi[0][0]), bl = smem_u32(&sl.Blo[0][0]);
-                const uint32_t d = tmem + (uint32_t)g * 128u;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {  // 8 pixels = 32 bytes inside the swizzled 128-byte rows
-                    const uint64_t a_hi = umma_desc(ah + k * 32, 16, 1024, kUmmaSw128), a_lo = umma_desc(al + k * 32, 16, 1024, kUmmaSw128);
-                    const uint64_t b_hi = umma_desc(bh + k * 32, 16, 1024, kUmmaSw128), b_lo = umma_desc(bl + k * 32, 16, 1024, kUmmaSw128);
-                    umma_tf32_ss(d, a_hi, b_hi, kIdesc, k == 0 ? 0u : 1u);
-                    umma_tf32_ss(d, a_hi, b_lo, kIdesc, 1u);
-                    umma_tf32_ss(d, a_lo, b_hi, kIdesc, 1u);
-                }
-                umma_commit(&sm.d_full[g]);
-            }
-            __syncwarp();
-            use[g]++;
-            g ^= 1;
+            mbar_arrive(&sm.d_full[g]);
         }
     } else if (warp >= kFbEpi0) {
         // ==================================================================== epilogue warps
@@ -422,7 +441,6 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
             }
             const int ch0 = *reinterpret_cast<volatile int32_t*>(&sm.ch0[g]);
             const int rows = min(32, cnt - 32 * ew);  // this warp's quarter of the accumulator: entries 32 ew .. 32 ew + 31
-            float(*tr)[kFbTrStride] = sm.tr[ew];
             if (rows > 0) {
 #pragma unroll 1
                 for (int j = 0; j < 4; j++) {
@@ -431,30 +449,55 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
                     tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 8; q++)
-                        *reinterpret_cast<float4*>(&tr[lane][j * 32 + q * 4]) =
+                        *reinterpret_cast<float4*>(&sm.tr[ew][lane][j * 32 + q * 4]) =
                             make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
                                         __uint_as_float(r[4 * q + 3]));
                 }
+                sm.tr_gid[ew][lane] = lane < rows ? sm.gid[g][32 * ew + lane] : 0u;
+                if (lane == 0) {
+                    sm.tr_rows[ew] = rows;
+                    sm.tr_ch0[ew] = ch0;
+                }
             }
-            const uint32_t my_gid = lane < rows ? sm.gid[g][32 * ew + lane] : 0u;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.d_empty[g]);  // accumulator and ids are out: the slot can be refilled
-            const bool col_ok = ch0 + lane * 4 < C;  // C % 4 == 0 on this path
-            float* dst = a.dL_dfeature + ch0 + lane * 4;
-            for (int r = 0; r < rows; r++) {
-                const uint32_t gid = __shfl_sync(0xffffffffu, my_gid, r);
-                if (col_ok) red_add_f4(dst + (size_t)gid * C, *reinterpret_cast<const float4*>(&tr[r][lane * 4]));
+            if (rows > 0) {
+                if (helpers) {
+                    pair_sync(ew);  // rows are in shared memory
+                    fb_reduce_rows(sm, ew, lane, 0, 2, rows, ch0, a);
+                    __syncwarp();
+                    pair_sync(ew);  // both halves are out: tr[ew] can be overwritten
+                } else {
+                    fb_reduce_rows(sm, ew, lane, 0, 1, rows, ch0, a);
+                    __syncwarp();
+                }
             }
-            __syncwarp();
             use[g]++;
             g ^= 1;
+        }
+        if (helpers) {
+            if (lane == 0) sm.tr_rows[ew] = -1;
+            __syncwarp();
+            pair_sync(ew);
+        }
+    } else if (helpers) {
+        // ==================================================================== helper warps
+        const int ew = warp - kFbHelp0;
+        for (;;) {
+            pair_sync(ew);
+            const int rows = *reinterpret_cast<volatile int32_t*>(&sm.tr_rows[ew]);
+            if (rows < 0) break;
+            const int ch0 = *reinterpret_cast<volatile int32_t*>(&sm.tr_ch0[ew]);
+            fb_reduce_rows(sm, ew, lane, 1, 2, rows, ch0, a);
+            __syncwarp();
+            pair_sync(ew);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kFbMmaWarp) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc<256>(tmem);
     }
@@ -518,7 +561,11 @@ cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const 
             sms_of_device[dev].store(n > 0 ? n : 148);
         }
         const int items = a.num_tiles * a.chunks * kBlocksPerTile;
-        feature_bwd_tc_kernel<<<min(items, sms_of_device[dev].load()), kFbThreads, smem, s>>>(a);
+        static const int helpers = [] {
+            const char* e = getenv("F3DGS_FBTC_HELPERS");
+            return e ? atoi(e) : 1;
+        }();
+        feature_bwd_tc_kernel<<<min(items, sms_of_device[dev].load()), kFbThreads, smem, s>>>(a, helpers);
         g_launches++;
         return cudaGetLastError();
     }

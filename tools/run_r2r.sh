@@ -4,9 +4,9 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
 timeout -s KILL 420 python -c "import torch; torch.zeros(8, device='cuda').sum().item()"
-for cfg in small200 small128 c3; do
+for cfg in small200 c3; do
   it=8; [ $cfg != c3 ] && it=2
-  timeout -s KILL 300 python tools/variant_times.py $cfg $it base base+fbtc > $O/r2r_$cfg.jsonl 2> $O/r2r_$cfg.err
+  timeout -s KILL 300 python tools/variant_times.py $cfg $it base base+fbtc base+fbtc+nohelp > $O/r2r_$cfg.jsonl 2> $O/r2r_$cfg.err
   echo "== $cfg rc=$?"
   python - $cfg <<'PY'
 import json, sys

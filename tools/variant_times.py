@@ -132,6 +132,9 @@ def main():
         if "+notc" in name:
             os.environ["F3DGS_TC"] = "0"
         os.environ.pop("F3DGS_FBWD_TC", None)
+        os.environ.pop("F3DGS_FBTC_HELPERS", None)
+        if "+nohelp" in name:
+            os.environ["F3DGS_FBTC_HELPERS"] = "0"
         if "+fbtc" in name:
             os.environ["F3DGS_FBWD_TC"] = "1"  # tensor-core feature-gradient kernel
         os.environ.pop("F3DGS_BWD2", None)
