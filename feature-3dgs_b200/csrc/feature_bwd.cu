@@ -13,6 +13,7 @@
 // entry.  No inter-warp synchronisation at all; 12 warps per SM.  Channel counts above 128 reuse the same lists for
 // every 128-channel chunk (the alpha evaluation is not repeated per chunk).
 // Reference semantics: backward.cu:565-575 (feature gradient; the feature loss does not feed dL/dalpha, :575 disabled).
+#include <cstdio>
 #include <cstdlib>
 
 #include "composite_common.cuh"
@@ -290,7 +291,16 @@ __device__ __forceinline__ void fb_reduce_rows(const FbSmem& sm, int ew, int lan
         red_add_f4(dst + (size_t)sm.tr_gid[ew][r] * a.C, *reinterpret_cast<const float4*>(&sm.tr[ew][r][lane * 4]));
 }
 
-__global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const FeatArgs a, const int helpers) {
+// development counters (F3DGS_FBTC_DIAG=1): cycles summed over CTAs -- loader group 0: loop, waiting for its slot;
+// epilogue warp 0: loop, waiting for an accumulator, transposing + reducing
+__device__ unsigned long long fbtc_diag[8];
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+constexpr int kFbHelpers = 1, kFbDiag = 2, kFbPrefetch = 4;
+
+__global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const FeatArgs a, const int flags) {
+    const int helpers = flags & kFbHelpers;
     extern __shared__ unsigned char fb_smem_dyn[];
     FbSmem& sm = *reinterpret_cast<FbSmem*>(fb_smem_dyn + ((1024u - (smem_u32(fb_smem_dyn) & 1023u)) & 1023u));
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -319,16 +329,37 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
         const int items = a.num_tiles * a.chunks * kBlocksPerTile;
         constexpr uint32_t kIdesc = umma_idesc_tf32(128, 128, 0, 0);
         uint32_t use = 0;
+        long long c_wait = 0;
+        const long long c_start = clock64();
+        // two items in hand: `item` is staged while the lists and gradient block of `next` are pulled into L2
         if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);
         group_sync(g);
         int item = sm.item[g];
-        while (item < items) {
-            group_sync(g);  // everyone has read the index
-            if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);  // the next one arrives while this one is staged
+        group_sync(g);
+        if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);
+        group_sync(g);
+        int next = sm.item[g];
+        size_t base = 0;
+        uint32_t n = 0;
+        if (item < items) {
             const ItemPos ip = decode_item(item, a);
             const uint32_t rx = a.ranges[ip.tile].x, ry = a.ranges[ip.tile].y;
-            const size_t base = 8 * (size_t)rx + (size_t)ip.b * (ry - rx);
-            const uint32_t n = a.list_cnt[(size_t)ip.tile * kBlocksPerTile + ip.b];
+            base = 8 * (size_t)rx + (size_t)ip.b * (ry - rx);
+            n = a.list_cnt[(size_t)ip.tile * kBlocksPerTile + ip.b];
+        }
+        while (item < items) {
+            group_sync(g);  // everyone has read the index
+            if (t == 0) sm.item[g] = atomicAdd(a.work_counter, 1);
+            const ItemPos ip = decode_item(item, a);
+            const bool has_next = next < items;
+            const ItemPos ip2 = decode_item(has_next ? next : 0, a);
+            size_t nbase = 0;
+            uint32_t nn = 0;
+            if (has_next) {
+                const uint32_t rx = a.ranges[ip2.tile].x, ry = a.ranges[ip2.tile].y;
+                nbase = 8 * (size_t)rx + (size_t)ip2.b * (ry - rx);
+                nn = a.list_cnt[(size_t)ip2.tile * kBlocksPerTile + ip2.b];
+            }
             for (uint32_t e0 = 0; e0 < n; e0 += kFbRows, use++) {
                 const uint32_t cnt = min((uint32_t)kFbRows, n - e0);
                 // ---- A: 128 list rows of 128 bytes; a warp instruction moves four rows (8 lanes x 16 bytes each).  Loaded
@@ -342,7 +373,20 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
                     if (row < (int)cnt) q[it] = __ldg(reinterpret_cast<const float4*>(wsrc + (size_t)row * 32) + (lane & 7));
                 }
                 const uint32_t my_gid = t < (int)cnt ? __ldg(&a.list_meta[base + e0 + t]).x : 0u;
+                if (e0 == 0 && has_next && (flags & kFbPrefetch)) {
+                    if ((uint32_t)t < nn) prefetch_l2(a.list_w + (nbase + t) * 32);
+                    if ((uint32_t)t + 128u < nn) prefetch_l2(a.list_w + (nbase + 128 + t) * 32);
+                    if ((uint32_t)t * 16u < min(nn, 256u)) prefetch_l2(a.list_meta + nbase + t * 16);
+                    const int ch2 = ip2.chunk * 128 + t;
+                    if (ch2 < C) {
+#pragma unroll
+                        for (int y = 0; y < 4; y++)
+                            if (ip2.by0 + y < H) prefetch_l2(a.dL_dfeat_pix + (size_t)ch2 * HW + (size_t)(ip2.by0 + y) * W + ip2.bx0);
+                    }
+                }
+                const long long c0 = clock64();
                 mbar_wait_sleep(&sm.d_empty[g], (use & 1u) ^ 1u, 32);
+                c_wait += clock64() - c0;
 #pragma unroll
                 for (int it = 0; it < kFbRows / 16; it++) {
                     const int row = it * 16 + gw * 4 + (lane >> 3), c16 = lane & 7;
@@ -414,7 +458,15 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
                 }
             }
             group_sync(g);
-            item = sm.item[g];
+            item = next;
+            next = sm.item[g];
+            base = nbase;
+            n = nn;
+        }
+        if ((flags & kFbDiag) && g == 0 && t == 0) {
+            atomicAdd(&fbtc_diag[0], (unsigned long long)(clock64() - c_start));
+            atomicAdd(&fbtc_diag[1], (unsigned long long)c_wait);
+            atomicAdd(&fbtc_diag[2], (unsigned long long)use);
         }
         // no more work for this group: tell the epilogue once the last accumulator has been read
         mbar_wait_sleep(&sm.d_empty[g], (use & 1u) ^ 1u, 32);
@@ -428,9 +480,14 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
         const int ew = warp - kFbEpi0;
         uint32_t use[kFbGroups] = {0, 0}, alive = (1u << kFbGroups) - 1;
         int g = 0;
+        long long c_wait = 0, c_red = 0;
+        const long long c_start = clock64();
         while (alive) {
             if (!((alive >> g) & 1u)) { g ^= 1; continue; }
+            const long long c0 = clock64();
             mbar_wait_sleep(&sm.d_full[g], use[g] & 1u, 32);
+            const long long c1 = clock64();
+            c_wait += c1 - c0;
             tc_fence_after();
             const int cnt = *reinterpret_cast<volatile int32_t*>(&sm.cnt[g]);
             if (cnt < 0) {
@@ -473,8 +530,14 @@ __global__ void __launch_bounds__(kFbThreads, 1) feature_bwd_tc_kernel(const Fea
                     __syncwarp();
                 }
             }
+            c_red += clock64() - c1;
             use[g]++;
             g ^= 1;
+        }
+        if ((flags & kFbDiag) && ew == 0 && lane == 0) {
+            atomicAdd(&fbtc_diag[3], (unsigned long long)(clock64() - c_start));
+            atomicAdd(&fbtc_diag[4], (unsigned long long)c_wait);
+            atomicAdd(&fbtc_diag[5], (unsigned long long)c_red);
         }
         if (helpers) {
             if (lane == 0) sm.tr_rows[ew] = -1;
@@ -561,13 +624,29 @@ cudaError_t launch_feature_bwd(const ViewParams& vp, const uint2* ranges, const 
             sms_of_device[dev].store(n > 0 ? n : 148);
         }
         const int items = a.num_tiles * a.chunks * kBlocksPerTile;
-        static const int helpers = [] {
-            const char* e = getenv("F3DGS_FBTC_HELPERS");
-            return e ? atoi(e) : 1;
+        static const int flags = [] {
+            auto on = [](const char* name, int dflt) {
+                const char* e = getenv(name);
+                return (e ? atoi(e) : dflt) != 0;
+            };
+            return (on("F3DGS_FBTC_HELPERS", 1) ? kFbHelpers : 0) | (on("F3DGS_FBTC_DIAG", 0) ? kFbDiag : 0) |
+                   (on("F3DGS_FBTC_PREFETCH", 1) ? kFbPrefetch : 0);
         }();
-        feature_bwd_tc_kernel<<<min(items, sms_of_device[dev].load()), kFbThreads, smem, s>>>(a, helpers);
+        const int grid = min(items, sms_of_device[dev].load());
+        feature_bwd_tc_kernel<<<grid, kFbThreads, smem, s>>>(a, flags);
         g_launches++;
-        return cudaGetLastError();
+        e = cudaGetLastError();
+        if (e == cudaSuccess && (flags & kFbDiag)) {  // development: per-CTA mean cycles of the roles, once per launch
+            unsigned long long d[8] = {0};
+            const unsigned long long zero[8] = {0};
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(d, fbtc_diag, sizeof(d));
+            cudaMemcpyToSymbol(fbtc_diag, zero, sizeof(zero));
+            fprintf(stderr, "fbtc_diag: loader0 loop %.0f wait_slot %.0f handovers %.1f | epi0 loop %.0f wait_acc %.0f drain %.0f (cycles per CTA, %d CTAs)\n",
+                    (double)d[0] / grid, (double)d[1] / grid, (double)d[2] / grid, (double)d[3] / grid, (double)d[4] / grid,
+                    (double)d[5] / grid, grid);
+        }
+        return e;
     }
     if (CH == 32) return launch_feat_bwd_t<32>(a, s);
     if (CH == 64) return launch_feat_bwd_t<64>(a, s);
