@@ -450,11 +450,11 @@ def test_view_batch_accumulates_like_autograd(name):
 
 # ------------------------------------------------------------------------------------------- per-process overrides
 @pytest.mark.parametrize("env", [{"F3DGS_TC": "0"}, {"F3DGS_BWD2": "0"}, {"F3DGS_TC": "0", "F3DGS_BWD2": "0"},
-                                 {"F3DGS_TC_MIN_C": "16"}])
+                                 {"F3DGS_TC_MIN_C": "16"}, {"F3DGS_FBWD_TC": "1"}])
 def test_kernel_selection_overrides_keep_parity(env):
-    """F3DGS_TC / F3DGS_BWD2 / F3DGS_TC_MIN_C are read once per process, so each setting runs in its own interpreter:
-    the fp32-pipe forward, the fused single-kernel backward and the tensor-core path at narrow widths must all pass the same
-    parity checks as the defaults."""
+    """F3DGS_TC / F3DGS_BWD2 / F3DGS_TC_MIN_C / F3DGS_FBWD_TC are read once per process, so each setting runs in its own
+    interpreter: the fp32-pipe forward, the fused single-kernel backward, the tensor-core path at narrow widths and the
+    opt-in tensor-core feature-gradient kernel must all pass the same parity checks as the defaults."""
     import os
     import subprocess
     import sys
