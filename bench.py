@@ -479,9 +479,10 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg[dom] / (per_launch[dom] * 1e-3) / 1e9 if per_launch[dom] > 0 else 0.0
-        traffic = None
+        traffic = None  # the ncu --set full capture under profiles/ was taken at config 3: null for the other configs
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            if args.config == "c3":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
         except Exception:
             pass
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
