@@ -100,6 +100,32 @@ def test_ply_and_feature_map_round_trip(tmp_path):
     assert torch.equal(io.load_feature_map(fpath), fm.half().float())
 
 
+def test_one_tap_gather_rule_holds_for_every_size():
+    """csrc/feature_head.cu picks the one-tap gather (`resize_bwd_one_kernel`) when both axis ratios are >= 2.001: it relies on
+    every source index being sampled by AT MOST ONE output index.  Checked here with the kernels' own float32 arithmetic
+    (make_geom: r = float(in - 1) / float(out - 1); src_of: s = r * float(o), i0 = int(s), i1 = i0 + (i0 < in - 1)) for
+    every output size up to 700 and a spread of ratios from the threshold upwards, including the reference's 1/2.25."""
+    rng = np.random.default_rng(7)
+    checked = 0
+    for n_out in list(range(2, 700, 3)) + [365, 549, 550]:
+        lo = int(np.ceil(2.001 * (n_out - 1))) + 1
+        cands = {lo, lo + 1, lo + 2, int(round(2.25 * n_out)), int(round(2.25 * n_out)) + 1, 3 * n_out, 4 * n_out + 1}
+        cands |= set(int(x) for x in rng.integers(lo, 6 * n_out + 8, size=4))
+        for n_src in cands:
+            r = np.float32(n_src - 1) / np.float32(n_out - 1)
+            if not r >= np.float32(2.001):
+                continue
+            o = np.arange(n_out, dtype=np.float32)
+            sp = (r * o).astype(np.float32)
+            i0 = sp.astype(np.int64)
+            i1 = i0 + (i0 < n_src - 1)
+            assert i0.min() >= 0 and i1.max() <= n_src - 1, (n_src, n_out)
+            # the tap sets {i0, i1} of consecutive outputs never touch: i0 strictly increases by at least 2
+            assert np.all(i0[1:] - i1[:-1] >= 1), (n_src, n_out)
+            checked += 1
+    assert checked > 1000
+
+
 # =================================================================================================== GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,size", SHAPES + [((128, 270, 480), (120, 160)), ((3, 45, 2101), (20, 900))])
